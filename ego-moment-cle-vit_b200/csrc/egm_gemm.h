@@ -1,0 +1,67 @@
+// Internal description of one batched GEMM-with-epilogue, shared by the two CUDA back
+// ends of the library:
+//   * egm_gemm_tc.cu   - tcgen05/TMEM tensor-core engine fed by TMA (bf16 hi/lo planes)
+//   * egm_gemm_simt.cu - fp32 FFMA engine for shapes TMA cannot address and for the
+//                        strict-fp32 mode
+//
+//   C[b] = alpha * alpha_b[b] * sum_t op(A_t[b]) * op(B_t[b])  +  beta_eye * I  +  gamma * E[b]
+//
+// Every dense contraction on the moment-pooling path (Gram matrices, W*Zc, Zc^T*U, the
+// Newton-Schulz chain and all of their backward products) is an instance of this.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace egm {
+
+// Precision modes of the path (public: the `precision_mode` argument of the C ABI).
+enum Precision : int {
+  PREC_FP32_SIMT = 0,  // fp32 FFMA on CUDA cores (exact fp32 products)
+  PREC_BF16X3 = 1,     // fp32 emulated on tcgen05: x = hi + lo (bf16 each), 3 MMAs per product
+  PREC_BF16 = 2,       // single bf16 MMA, fp32 accumulate
+};
+
+// Batched row-major matrix view [batch][rows][cols].
+// fp32 storage : p0 = float*,  p1 unused.
+// plane storage: p0 = bf16 "hi" plane, p1 = bf16 "lo" plane (x ~= hi + lo), same ld/bstride.
+struct Mat {
+  void* p0 = nullptr;
+  void* p1 = nullptr;
+  int rows = 0, cols = 0;
+  long long ld = 0;       // elements between consecutive rows
+  long long bstride = 0;  // elements between consecutive batch items
+};
+
+struct GemmTerm {
+  Mat A;       // op(A) is M x K : stored [M,K] (transA = 0) or [K,M] (transA = 1)
+  int transA = 0;
+  Mat B;       // op(B) is K x N : stored [K,N] (transB = 0) or [N,K] (transB = 1)
+  int transB = 0;
+  int K = 0;
+};
+
+struct GemmProblem {
+  int M = 0, N = 0, batch = 1;
+  int nterms = 1;
+  GemmTerm t[2];
+  // epilogue
+  float alpha = 1.f;
+  const float* alpha_b = nullptr;  // optional per-batch multiplier (device pointer)
+  float beta_eye = 0.f;
+  float gamma = 0.f;
+  Mat E;             // optional addend, storage given by e_planes
+  int e_planes = 0;
+  Mat Cp;            // optional output as bf16 planes (p0 == nullptr: absent)
+  Mat Cf;            // optional output as fp32       (p0 == nullptr: absent)
+};
+
+// Returns cudaSuccess or the launch error. No allocation, no synchronisation.
+cudaError_t gemm_tc(const GemmProblem& g, int npass /*1 or 3*/, cudaStream_t stream);
+cudaError_t gemm_simt(const GemmProblem& g, cudaStream_t stream);  // all Mats fp32
+// True when every operand of `g` satisfies the TMA addressing rules of the tcgen05 engine.
+bool gemm_tc_supported(const GemmProblem& g, int npass);
+
+const char* last_error();
+void set_error(const char* fmt, ...);
+
+}  // namespace egm

@@ -1,0 +1,521 @@
+// tcgen05 / TMEM batched GEMM engine of the moment-pooling path (sm_100a only).
+//
+// Replaces, for every dense contraction of the path, what the reference leaves to
+// torch.bmm -> cuBLAS (reference: src/models/moment_head.py:53-64 Newton-Schulz loop,
+// :292-293 pooling products, src/models/gpf_kernel.py:88 Gram) and the elementwise passes
+// around them (`3*I - ZY`, `0.5 *`, `/ sqrt(trace)`), which are folded into the epilogue.
+//
+// Shape of the kernel (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 3-D boxes {64 x rows x 1 image} of the
+//               bf16 operand planes into 128B-swizzled shared memory, mbarrier-signalled
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::f16 (128 x 256 x 16 per
+//               instruction) into one of two 256-column fp32 accumulators in TMEM
+//   warps 2..5  epilogue: tcgen05.ld the finished accumulator (32 lanes x 32 columns per
+//               load), apply  alpha*acc + beta*I + gamma*E, split to bf16 hi/lo planes and/or
+//               write fp32, while the MMA warp is already filling the other accumulator
+//
+// fp32 fidelity ("bf16x3"): every fp32 operand x is carried as two bf16 planes
+// hi = bf16(x), lo = bf16(x - hi).  A*B ~= Ah*Bh + Ah*Bl + Al*Bh  (3 MMAs, fp32 accumulate,
+// relative error ~1e-5).  The single-pass mode issues Ah*Bh only.
+//
+// Up to two products are accumulated into the same TMEM tile (C = A0*B0 + A1*B1), which
+// is what the Newton-Schulz backward needs (e.g. dY = dY'*T^T + Z^T*dP) without a
+// read-modify-write epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "egm_gemm.h"
+#include "egm_ptx.cuh"
+
+namespace egm {
+
+namespace {
+
+constexpr int BM = 128;        // tile rows  (= UMMA M, one TMEM lane per row)
+constexpr int BN = 256;        // tile cols  (= UMMA N, one TMEM column per col)
+constexpr int BK = 64;         // K per pipeline stage: 64 bf16 = one 128-byte swizzle line
+constexpr int UK = 16;         // K per tcgen05.mma (bf16)
+constexpr int kTileA = BM * BK * 2;   // 16 KiB per plane
+constexpr int kTileB = BN * BK * 2;   // 32 KiB per plane
+constexpr int kChunk = BK * 128;      // one MN-major TMA box: 64 K-rows x 128 B = 8 KiB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;        // two 256-column accumulators
+
+struct alignas(64) TcParams {
+  CUtensorMap tm[2][4];  // [term][A_hi, A_lo, B_hi, B_lo]
+  int M, N, batch, nterms;
+  int K[2], a_mn[2], b_mn[2];
+  int tiles_m, tiles_n;
+  float alpha, beta_eye, gamma;
+  const float* alpha_b;
+  const void* E0;
+  const void* E1;
+  long long ldE, bsE;
+  int e_mode;  // 0 none, 1 bf16 planes, 2 fp32
+  __nv_bfloat16* Cp_hi;
+  __nv_bfloat16* Cp_lo;
+  long long ldCp, bsCp;
+  float* Cf;
+  long long ldCf, bsCf;
+};
+
+template <int NPASS>
+struct Cfg {
+  static constexpr int kPlanes = (NPASS == 3) ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kTileA + kTileB);      // 96 KiB / 48 KiB
+  static constexpr int kStages = (NPASS == 3) ? 2 : 4;                 // 192 KiB of operands
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
+         (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using C = Cfg<NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms are 1024 B: align the operand ring.
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  // barrier block: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes +
+                                           8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < p.nterms; ++t)
+      for (int i = 0; i < 4; ++i)
+        if (i % 2 == 0 || NPASS == 3) ptx::prefetch_tensormap(&p.tm[t][i]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::kStages; ++s) {
+        ptx::mbar_init(full_bar(s), 1);
+        ptx::mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);
+        ptx::mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int tiles_per_img = p.tiles_m * p.tiles_n;
+  const int ntiles = tiles_per_img * p.batch;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int m0 = (r / p.tiles_n) * BM;
+        const int n0 = (r % p.tiles_n) * BN;
+        for (int t = 0; t < p.nterms; ++t) {
+          const int nkb = (p.K[t] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t fb = full_bar(stage);
+            ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
+            const uint32_t sA = smem_base + stage * C::kStageBytes;
+            const uint32_t sB = sA + C::kPlanes * kTileA;
+            const int k0 = kb * BK;
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl) {
+              if (!p.a_mn[t]) {
+                ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, b);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j)
+                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j,
+                                   k0, b);
+              }
+              if (!p.b_mn[t]) {
+                ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, b);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk,
+                                   n0 + 64 * j, k0, b);
+              }
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int t = 0; t < p.nterms; ++t) {
+          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
+          const uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, a_mn, b_mn);
+          const uint32_t a_step = a_mn ? 2048u : 32u;   // bytes per 16-wide K step
+          const uint32_t b_step = b_mn ? 2048u : 32u;
+          const uint32_t a_lbo = a_mn ? kChunk : 0u;
+          const uint32_t b_lbo = b_mn ? kChunk : 0u;
+          const int nkb = (p.K[t] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sA = smem_base + stage * C::kStageBytes;
+            const uint32_t sB = sA + C::kPlanes * kTileA;
+#pragma unroll
+            for (int kk = 0; kk < BK / UK; ++kk) {
+              const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
+              const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
+              if (NPASS == 3) {
+                const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
+                const uint64_t bl = ptx::smem_desc_sw128(sB + kTileB + kk * b_step, b_lbo, 1024);
+                ptx::mma_bf16_ss(d_tmem, al, bh, idesc, accumulate);
+                ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
+                ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
+              } else {
+                ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, accumulate);
+              }
+              accumulate = 1u;
+            }
+            ptx::tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        ptx::tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int m0 = (r / p.tiles_n) * BM;
+      const int n0 = (r % p.tiles_n) * BN;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
+        if (p.beta_eye != 0.f) {
+          const int d = row - col0;
+          if (d >= 0 && d < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == d) o[j] += p.beta_eye;
+          }
+        }
+        const bool full = (col0 + 32 <= p.N);
+        if (p.e_mode == 1) {
+          const __nv_bfloat16* eh =
+              static_cast<const __nv_bfloat16*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
+          const __nv_bfloat16* el =
+              p.E1 ? static_cast<const __nv_bfloat16*>(p.E1) + b * p.bsE + (long long)row * p.ldE + col0
+                   : nullptr;
+          if (full && (p.ldE & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 h = __ldg(reinterpret_cast<const uint4*>(eh) + j);
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                o[j * 8 + 2 * w] += p.gamma * __uint_as_float(hw[w] << 16);
+                o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
+              }
+              if (el) {
+                uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
+                const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  o[j * 8 + 2 * w] += p.gamma * __uint_as_float(lw[w] << 16);
+                  o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                float e = __bfloat162float(eh[j]);
+                if (el) e += __bfloat162float(el[j]);
+                o[j] += p.gamma * e;
+              }
+          }
+        } else if (p.e_mode == 2) {
+          const float* ef = static_cast<const float*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
+          if (full && (p.ldE & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 e = __ldg(reinterpret_cast<const float4*>(ef) + j);
+              o[4 * j] += p.gamma * e.x;
+              o[4 * j + 1] += p.gamma * e.y;
+              o[4 * j + 2] += p.gamma * e.z;
+              o[4 * j + 3] += p.gamma * e.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] += p.gamma * ef[j];
+          }
+        }
+        if (p.Cp_hi) {
+          __nv_bfloat16* ch = p.Cp_hi + b * p.bsCp + (long long)row * p.ldCp + col0;
+          __nv_bfloat16* cl = p.Cp_lo ? p.Cp_lo + b * p.bsCp + (long long)row * p.ldCp + col0 : nullptr;
+          if (full && (p.ldCp & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(o[j * 8 + 2 * w], h0, l0);
+                split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
+                hw[w] = pack2(h0, h1);
+                lw[w] = pack2(l0, l1);
+              }
+              reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (cl) reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                __nv_bfloat16 h, l;
+                split_bf16(o[j], h, l);
+                ch[j] = h;
+                if (cl) cl[j] = l;
+              }
+          }
+        }
+        if (p.Cf) {
+          float* cf = p.Cf + b * p.bsCf + (long long)row * p.ldCf + col0;
+          if (full && (p.ldCf & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(cf)[j] =
+                  make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) cf[j] = o[j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  // libcuda is not linked (the library is built on a GPU-less box): resolve at run time.
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) !=
+            cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// bf16 plane [batch][rows][cols] -> 3-D tiled map with a {64, box_rows, 1} box, 128B swizzle.
+// Out-of-range box elements read as zero, so ragged M/N/K edges need no special casing.
+bool make_plane_map(CUtensorMap* tm, const void* base, const Mat& m, int batch, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return false;
+  }
+  const long long bs = (batch > 1) ? m.bstride : (long long)m.rows * m.ld;
+  cuuint64_t dims[3] = {(cuuint64_t)m.cols, (cuuint64_t)m.rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)m.ld * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%d cols=%d ld=%lld bstride=%lld batch=%d",
+              (int)r, m.rows, m.cols, m.ld, bs, batch);
+    return false;
+  }
+  return true;
+}
+
+bool plane_ok(const Mat& m, int batch, bool need_lo) {
+  if (!m.p0 || (need_lo && !m.p1)) return false;
+  if ((reinterpret_cast<uintptr_t>(m.p0) & 15) || (need_lo && (reinterpret_cast<uintptr_t>(m.p1) & 15)))
+    return false;
+  if (m.ld % 8 != 0 || m.ld < m.cols) return false;
+  if (batch > 1 && (m.bstride % 8 != 0 || m.bstride <= 0)) return false;
+  return true;
+}
+
+template <int NPASS>
+cudaError_t launch(const TcParams& p, cudaStream_t stream) {
+  using C = Cfg<NPASS>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (configured_dev != dev) {
+    e = cudaFuncSetAttribute(gemm_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  int sms = 0;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  gemm_tc_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmProblem& g, int npass) {
+  const bool lo = (npass == 3);
+  for (int t = 0; t < g.nterms; ++t) {
+    if (!plane_ok(g.t[t].A, g.batch, lo) || !plane_ok(g.t[t].B, g.batch, lo)) return false;
+  }
+  if (g.Cp.p0 && (g.Cp.ld < g.N)) return false;
+  return g.M > 0 && g.N > 0 && g.batch > 0;
+}
+
+cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
+  if (npass != 1 && npass != 3) {
+    set_error("gemm_tc: npass must be 1 or 3");
+    return cudaErrorInvalidValue;
+  }
+  if (g.nterms < 1 || g.nterms > 2 || !gemm_tc_supported(g, npass)) {
+    set_error("gemm_tc: operand layout not addressable by TMA (need 16B-aligned planes, ld%%8==0)");
+    return cudaErrorInvalidValue;
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M;
+  p.N = g.N;
+  p.batch = g.batch;
+  p.nterms = g.nterms;
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  for (int t = 0; t < g.nterms; ++t) {
+    const GemmTerm& gt = g.t[t];
+    p.K[t] = gt.K;
+    p.a_mn[t] = gt.transA ? 1 : 0;   // stored [K,M]  -> M-major
+    p.b_mn[t] = gt.transB ? 0 : 1;   // stored [K,N]  -> N-major ; [N,K] -> K-major
+    const int a_rows = gt.transA ? BK : BM;
+    const int b_rows = gt.transB ? BN : BK;
+    // logical extents double as the TMA bounds: whatever lies outside reads as zero
+    Mat A = gt.A, B = gt.B;
+    A.rows = gt.transA ? gt.K : g.M;
+    A.cols = gt.transA ? g.M : gt.K;
+    B.rows = gt.transB ? g.N : gt.K;
+    B.cols = gt.transB ? gt.K : g.N;
+    if (!make_plane_map(&p.tm[t][0], A.p0, A, g.batch, a_rows)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&p.tm[t][2], B.p0, B, g.batch, b_rows)) return cudaErrorInvalidValue;
+    if (npass == 3) {
+      if (!make_plane_map(&p.tm[t][1], A.p1, A, g.batch, a_rows)) return cudaErrorInvalidValue;
+      if (!make_plane_map(&p.tm[t][3], B.p1, B, g.batch, b_rows)) return cudaErrorInvalidValue;
+    }
+  }
+  p.alpha = g.alpha;
+  p.alpha_b = g.alpha_b;
+  p.beta_eye = g.beta_eye;
+  p.gamma = g.gamma;
+  if (g.E.p0 && g.gamma != 0.f) {
+    p.E0 = g.E.p0;
+    p.E1 = g.e_planes ? g.E.p1 : nullptr;
+    p.ldE = g.E.ld;
+    p.bsE = g.E.bstride;
+    p.e_mode = g.e_planes ? 1 : 2;
+  }
+  if (g.Cp.p0) {
+    p.Cp_hi = static_cast<__nv_bfloat16*>(g.Cp.p0);
+    p.Cp_lo = static_cast<__nv_bfloat16*>(g.Cp.p1);
+    p.ldCp = g.Cp.ld;
+    p.bsCp = g.Cp.bstride;
+  }
+  if (g.Cf.p0) {
+    p.Cf = static_cast<float*>(g.Cf.p0);
+    p.ldCf = g.Cf.ld;
+    p.bsCf = g.Cf.bstride;
+  }
+  return npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
+}
+
+}  // namespace egm
