@@ -1,0 +1,620 @@
+// C ABI of the library (include/egm_b200.h): the chains of GEMM-engine launches and
+// bandwidth kernels that make up each operator of the moment-pooling path.
+//
+// Arithmetic follows SURVEY.md Appendix A. Newton-Schulz uses the commuting form
+//   P_k = Z_k Y_k,  T_k = 1.5 I - 0.5 P_k,  Y_{k+1} = Y_k T_k,  Z_{k+1} = T_k Z_k
+// (Y_k, Z_k are polynomials in A, so Y_k Z_k = Z_k Y_k for ANY input A): 3K-3 GEMMs forward
+// and 6K-6 backward for K >= 2 instead of the reference's 4K / 8K (moment_head.py:53-64).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/egm_b200.h"
+#include "egm_gemm.h"
+#include "egm_kernels.cuh"
+
+using namespace egm;
+
+namespace {
+
+struct Arena {
+  uint8_t* p;
+  size_t cap, used;
+  Arena(void* base, size_t bytes) : p(static_cast<uint8_t*>(base)), cap(bytes), used(0) {}
+  void* take(size_t bytes) {
+    const size_t a = (used + 255) & ~size_t(255);
+    used = a + bytes;
+    return (used <= cap && p) ? p + a : nullptr;
+  }
+};
+inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+bool prec_ok(int prec) { return prec == PREC_FP32_SIMT || prec == PREC_BF16X3 || prec == PREC_BF16; }
+
+cudaError_t run_gemm(const GemmProblem& g, int prec, cudaStream_t st) {
+  if (prec == PREC_FP32_SIMT) return gemm_simt(g, st);
+  return gemm_tc(g, prec == PREC_BF16X3 ? 3 : 1, st);
+}
+// route a working-matrix output / addend to the right slot of the problem
+void out_w(GemmProblem& g, const W& w, int prec) {
+  if (prec == PREC_FP32_SIMT) g.Cf = w_mat(w, prec); else g.Cp = w_mat(w, prec);
+}
+void addend_w(GemmProblem& g, const W& w, float gamma, int prec) {
+  g.E = w_mat(w, prec);
+  g.e_planes = (prec != PREC_FP32_SIMT);
+  g.gamma = gamma;
+}
+GemmTerm term(const W& A, int tA, const W& B, int tB, int K, int prec) {
+  GemmTerm t;
+  t.A = w_mat(A, prec); t.transA = tA; t.B = w_mat(B, prec); t.transB = tB; t.K = K;
+  return t;
+}
+
+#define EGM_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      set_error(__VA_ARGS__);          \
+      return code;                     \
+    }                                  \
+  } while (0)
+#define EGM_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      set_error("%s: %s [%s]", #expr, cudaGetErrorString(e_), last_error());        \
+      return EGM_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+#define EGM_LAUNCHED() EGM_CUDA(cudaGetLastError())
+
+// -------------------------------------------------------------- NS state layout
+// K iterations store: A, T_0..T_{K-1}, Z_1..Z_{K-1}, Y_2..Y_{K-1}  (Y_1 == T_0)
+struct NsState {
+  int B, D, K;
+  uint8_t* base;
+  size_t each;
+  NsState(void* s, int B_, int D_, int K_) : B(B_), D(D_), K(K_), base(static_cast<uint8_t*>(s)) {
+    each = pad256(w_bytes(B, D, D));
+  }
+  static int count(int K) { return K <= 0 ? 1 : 1 + K + (K > 1 ? K - 1 : 0) + (K > 2 ? K - 2 : 0); }
+  W slot(int i) const { return make_w(base + (size_t)i * each, B, D, D); }
+  W A() const { return slot(0); }
+  W T(int k) const { return slot(1 + k); }
+  W Z(int k) const { return slot(1 + K + (k - 1)); }                  // k in [1, K-1]
+  W Y(int k) const { return k == 1 ? T(0) : slot(1 + K + (K - 1) + (k - 2)); }  // k in [1, K-1]
+};
+
+}  // namespace
+
+extern "C" {
+
+int egm_version(void) { return 100; }
+const char* egm_last_error(void) { return last_error(); }
+
+// =========================================================================== GPF
+long long egm_gpf_ldr(int N) { return ((long long)N + 3) / 4 * 4; }
+
+size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec) {
+  (void)prec;
+  return 2 * pad256(w_bytes(B, N, D)) + 512;
+}
+
+int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
+                int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
+                float* nrm_p, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_fwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(a && p && coef && G && Ra && Rp && nrm_a && nrm_p, EGM_ERR_ARG, "egm_gpf_fwd: null pointer");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && P >= 0 && Q >= 0 && P <= 15 && Q <= 15, EGM_ERR_ARG,
+              "egm_gpf_fwd: bad sizes B=%d N=%d D=%d P=%d Q=%d (degrees 0..15)", B, N, D, P, Q);
+  Arena ar(ws, ws_bytes);
+  void* wa = ar.take(w_bytes(B, N, D));
+  void* wp = ar.take(w_bytes(B, N, D));
+  EGM_REQUIRE(wa && wp, EGM_ERR_WORKSPACE, "egm_gpf_fwd: workspace %zu < %zu", ws_bytes,
+              egm_gpf_fwd_workspace(B, N, D, prec));
+  const long long ldR = egm_gpf_ldr(N);
+  const W An = make_w(wa, B, N, D), Pn = make_w(wp, B, N, D);
+  k::rownorm(a, B, N, D, eps, cosine, nrm_a, An, prec, st);
+  k::rownorm(p, B, N, D, eps, cosine, nrm_p, Pn, prec, st);
+  EGM_LAUNCHED();
+  for (int v = 0; v < 2; ++v) {
+    GemmProblem g;
+    g.M = N; g.N = N; g.batch = B; g.nterms = 1;
+    g.t[0] = term(v ? Pn : An, 0, v ? Pn : An, 1, D, prec);
+    g.Cf = f32_mat(v ? Rp : Ra, N, N, ldR, (long long)N * ldR);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  k::gpf_poly_fwd(Ra, Rp, ldR, coef, P, Q, symmetric, B, N, G, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+size_t egm_gpf_bwd_workspace(int B, int N, int D, int P, int Q, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, N, D)) + 2 * pad256(w_bytes(B, N, N)) + pad256((size_t)B * N * D * 4) +
+         pad256((size_t)k::gpf_poly_bwd_blocks(B, N) * (P + 1) * (Q + 1) * 4) + 1024;
+}
+
+int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* coef, const float* Ra,
+                const float* Rp, const float* nrm_a, const float* nrm_p, int B, int N, int D, int P,
+                int Q, int cosine, float eps, int symmetric, float* da, float* dp, float* dcoef,
+                int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_bwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(dG && a && p && coef && Ra && Rp && nrm_a && nrm_p && da && dp && dcoef, EGM_ERR_ARG,
+              "egm_gpf_bwd: null pointer");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && P >= 0 && Q >= 0 && P <= 15 && Q <= 15, EGM_ERR_ARG,
+              "egm_gpf_bwd: bad sizes");
+  Arena ar(ws, ws_bytes);
+  void* wx = ar.take(w_bytes(B, N, D));
+  void* wea = ar.take(w_bytes(B, N, N));
+  void* wep = ar.take(w_bytes(B, N, N));
+  float* dxn = static_cast<float*>(ar.take((size_t)B * N * D * 4));
+  const int nblocks = k::gpf_poly_bwd_blocks(B, N);
+  float* partial = static_cast<float*>(ar.take((size_t)nblocks * (P + 1) * (Q + 1) * 4));
+  EGM_REQUIRE(wx && wea && wep && dxn && partial, EGM_ERR_WORKSPACE, "egm_gpf_bwd: workspace %zu < %zu",
+              ws_bytes, egm_gpf_bwd_workspace(B, N, D, P, Q, prec));
+  const long long ldR = egm_gpf_ldr(N);
+  const W Ea = make_w(wea, B, N, N), Ep = make_w(wep, B, N, N), Xn = make_w(wx, B, N, D);
+  k::gpf_poly_bwd(dG, Ra, Rp, ldR, coef, P, Q, symmetric, B, N, Ea, Ep, partial, nblocks, dcoef, prec, st);
+  EGM_LAUNCHED();
+  for (int v = 0; v < 2; ++v) {
+    const float* x = v ? p : a;
+    const float* nrm = v ? nrm_p : nrm_a;
+    float* dx = v ? dp : da;
+    // re-materialise the normalised tokens (cheaper than keeping 2 x [B,N,D] alive)
+    k::rownorm(x, B, N, D, eps, cosine, dxn /*norms scratch, overwritten below*/, Xn, prec, st);
+    EGM_LAUNCHED();
+    GemmProblem g;  // d An = (dR + dR^T) An
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(v ? Ep : Ea, 0, Xn, 0, N, prec);
+    g.Cf = f32_mat(cosine ? dxn : dx, N, D, D, (long long)N * D);
+    EGM_CUDA(run_gemm(g, prec, st));
+    if (cosine) {
+      k::rownorm_bwd(x, nrm, dxn, B, N, D, eps, dx, st);
+      EGM_LAUNCHED();
+    }
+  }
+  return EGM_OK;
+}
+
+// ========================================================================== pool
+size_t egm_pool_state_bytes(int B, int N, int D, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, N, N)) + pad256(w_bytes(B, N, D)) + 256;
+}
+size_t egm_pool_fwd_workspace(int B, int N, int D, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, N, D)) + 512;
+}
+
+int egm_pool_fwd(const float* Z, const float* G, int B, int N, int D, float eps, float* M2, float* u,
+                 float* vecs, float* mu, void* state, int prec, void* ws, size_t ws_bytes,
+                 egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_pool_fwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(Z && G && M2 && vecs && mu && state, EGM_ERR_ARG, "egm_pool_fwd: null pointer");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0, EGM_ERR_ARG, "egm_pool_fwd: bad sizes");
+  Arena sa(state, egm_pool_state_bytes(B, N, D, prec));
+  const W Wn = make_w(sa.take(w_bytes(B, N, N)), B, N, N);
+  const W Zc = make_w(sa.take(w_bytes(B, N, D)), B, N, D);
+  Arena ar(ws, ws_bytes);
+  void* wu = ar.take(w_bytes(B, N, D));
+  EGM_REQUIRE(wu, EGM_ERR_WORKSPACE, "egm_pool_fwd: workspace %zu < %zu", ws_bytes,
+              egm_pool_fwd_workspace(B, N, D, prec));
+  const W U = make_w(wu, B, N, D);
+  float* s = vecs;
+  float* deg = vecs + (size_t)B * N;
+  float* w = vecs + (size_t)2 * B * N;
+  float* wdiag = vecs + (size_t)3 * B * N;
+  float* t = vecs + (size_t)4 * B * N;
+  float* sw = t + B;
+  k::degree(G, B, N, eps, deg, s, st);
+  k::weight(G, s, B, N, Wn, w, wdiag, prec, st);
+  k::mean_center(Z, w, wdiag, B, N, D, eps, t, sw, mu, u, Zc, prec, st);
+  EGM_LAUNCHED();
+  {
+    GemmProblem g;  // U = Wn Zc
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Wn, 0, Zc, 0, N, prec);
+    out_w(g, U, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // M2 = Zc^T U
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 1, U, 0, N, prec);
+    g.Cf = f32_mat(M2, D, D, D, (long long)D * D);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  return EGM_OK;
+}
+
+size_t egm_pool_bwd_workspace(int B, int N, int D, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, D, D)) + 2 * pad256(w_bytes(B, N, D)) + pad256((size_t)B * N * D * 4) +
+         pad256((size_t)B * N * egm_gpf_ldr(N) * 4) + pad256((size_t)B * D * 4) +
+         3 * pad256((size_t)B * N * 4) + 2048;
+}
+
+int egm_pool_bwd(const float* dM2, const float* du, const float* Z, const float* G, const float* u,
+                 const float* vecs, const float* mu, const void* state, int B, int N, int D, float eps,
+                 float* dZ, float* dG, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_pool_bwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(dM2 && Z && G && vecs && mu && state && dZ && dG, EGM_ERR_ARG, "egm_pool_bwd: null pointer");
+  EGM_REQUIRE(!du || u, EGM_ERR_ARG, "egm_pool_bwd: du given without u");
+  Arena sa(const_cast<void*>(state), egm_pool_state_bytes(B, N, D, prec));
+  const W Wn = make_w(sa.take(w_bytes(B, N, N)), B, N, N);
+  const W Zc = make_w(sa.take(w_bytes(B, N, D)), B, N, D);
+  Arena ar(ws, ws_bytes);
+  void* wdm = ar.take(w_bytes(B, D, D));
+  void* wv1 = ar.take(w_bytes(B, N, D));
+  void* wv2 = ar.take(w_bytes(B, N, D));
+  float* dZc = static_cast<float*>(ar.take((size_t)B * N * D * 4));
+  const long long ldW = egm_gpf_ldr(N);
+  float* dW = static_cast<float*>(ar.take((size_t)B * N * ldW * 4));
+  float* dmu = static_cast<float*>(ar.take((size_t)B * D * 4));
+  float* dw = static_cast<float*>(ar.take((size_t)B * N * 4));
+  float* ds = static_cast<float*>(ar.take((size_t)B * N * 4));
+  float* dt = static_cast<float*>(ar.take((size_t)B * N * 4));
+  EGM_REQUIRE(wdm && wv1 && wv2 && dZc && dW && dmu && dw && ds && dt, EGM_ERR_WORKSPACE,
+              "egm_pool_bwd: workspace %zu < %zu", ws_bytes, egm_pool_bwd_workspace(B, N, D, prec));
+  const float* s = vecs;
+  const float* deg = vecs + (size_t)B * N;
+  const float* w = vecs + (size_t)2 * B * N;
+  const float* t = vecs + (size_t)4 * B * N;
+  const float* sw = t + B;
+  const W dMw = make_w(wdm, B, D, D), V1 = make_w(wv1, B, N, D), V2 = make_w(wv2, B, N, D);
+  k::affine(dM2, D, (long long)D * D, B, D, D, nullptr, 1.f, 0.f, dMw, 0.f, 0.f, nullptr, prec, st);
+  EGM_LAUNCHED();
+  {
+    GemmProblem g;  // V1 = Zc dM^T
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 0, dMw, 1, D, prec);
+    out_w(g, V1, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // V2 = Zc dM
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 0, dMw, 0, D, prec);
+    out_w(g, V2, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // dZc = Wn V1 + Wn^T V2
+    g.M = N; g.N = D; g.batch = B; g.nterms = 2;
+    g.t[0] = term(Wn, 0, V1, 0, N, prec);
+    g.t[1] = term(Wn, 1, V2, 0, N, prec);
+    g.Cf = f32_mat(dZc, N, D, D, (long long)N * D);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // dW = V2 Zc^T
+    g.M = N; g.N = N; g.batch = B; g.nterms = 1;
+    g.t[0] = term(V2, 0, Zc, 1, D, prec);
+    g.Cf = f32_mat(dW, N, N, ldW, (long long)N * ldW);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  k::pool_bwd_dmu(dZc, du, sw, t, B, N, D, eps, dmu, st);
+  k::pool_bwd_rows(dZc, Z, Zc, w, t, mu, u, du, dmu, B, N, D, eps, dZ, dw, dt, prec, st);
+  k::pool_bwd_ds(dW, ldW, dw, dt, G, s, B, N, ds, st);
+  k::pool_bwd_dG(dW, ldW, dw, dt, s, deg, ds, B, N, eps, dG, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+// ============================================================================ NS
+size_t egm_ns_state_bytes(int B, int D, int iters, int prec) {
+  (void)prec;
+  return (size_t)NsState::count(iters) * pad256(w_bytes(B, D, D)) + 256;
+}
+size_t egm_ns_fwd_workspace(int B, int D, int iters, int prec) {
+  (void)iters; (void)prec;
+  return 2 * pad256(w_bytes(B, D, D)) + 512;
+}
+
+int egm_ns_fwd(const float* M, int B, int D, int iters, float eps, int post_mode, float* O,
+               float* scal, void* state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_ns_fwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(M && O && scal && state, EGM_ERR_ARG, "egm_ns_fwd: null pointer");
+  EGM_REQUIRE(B > 0 && D > 0 && iters >= 0 && iters <= 64, EGM_ERR_ARG, "egm_ns_fwd: bad sizes");
+  EGM_REQUIRE(post_mode == 0 || post_mode == 1, EGM_ERR_ARG, "egm_ns_fwd: post_mode must be 0 or 1");
+  const int K = iters;
+  NsState S(state, B, D, K);
+  Arena ar(ws, ws_bytes);
+  void* wy = ar.take(w_bytes(B, D, D));
+  EGM_REQUIRE(wy, EGM_ERR_WORKSPACE, "egm_ns_fwd: workspace %zu < %zu", ws_bytes,
+              egm_ns_fwd_workspace(B, D, iters, prec));
+  float* tr = scal;
+  float* inv = scal + B;
+  float* post = scal + 2 * B;
+  const long long dd = (long long)D * D;
+  k::trace_scales(M, B, D, eps, post_mode, tr, inv, post, st);
+  // A = M/(tr+eps) and T_0 = 1.5 I - 0.5 A in one pass over M
+  const W A = S.A();
+  if (K >= 1) {
+    const W T0 = S.T(0);
+    k::affine(M, D, dd, B, D, D, inv, 1.f, 0.f, A, -0.5f, 1.5f, &T0, prec, st);
+  } else {
+    k::affine(M, D, dd, B, D, D, inv, 1.f, 0.f, A, 0.f, 0.f, nullptr, prec, st);
+  }
+  EGM_LAUNCHED();
+  if (K <= 1) {
+    // no product needed: Y_0 = I, Y_1 = 1.5 I - 0.5 A.  O = post * Y_K in fp32.
+    W Yf;
+    Yf.base = wy; Yf.rows = D; Yf.cols = D; Yf.ld = D; Yf.batch = B;
+    W Ow = Yf;
+    Ow.base = O;
+    k::affine(M, D, dd, B, D, D, inv, K == 1 ? -0.5f : 0.f, K == 1 ? 1.5f : 1.f, Yf, 0.f, 0.f, nullptr,
+              PREC_FP32_SIMT, st);
+    k::affine(static_cast<const float*>(wy), D, dd, B, D, D, post, 1.f, 0.f, Ow, 0.f, 0.f, nullptr,
+              PREC_FP32_SIMT, st);
+    EGM_LAUNCHED();
+    return EGM_OK;
+  }
+  // Z_1 = T_0 A
+  {
+    GemmProblem g;
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(S.T(0), 0, A, 0, D, prec);
+    out_w(g, S.Z(1), prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  for (int k = 1; k <= K - 1; ++k) {
+    {
+      GemmProblem g;  // T_k = 1.5 I - 0.5 Z_k Y_k
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(S.Z(k), 0, S.Y(k), 0, D, prec);
+      g.alpha = -0.5f; g.beta_eye = 1.5f;
+      out_w(g, S.T(k), prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    if (k < K - 1) {
+      {
+        GemmProblem g;  // Y_{k+1} = Y_k T_k
+        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+        g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+        out_w(g, S.Y(k + 1), prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      {
+        GemmProblem g;  // Z_{k+1} = T_k Z_k
+        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+        g.t[0] = term(S.T(k), 0, S.Z(k), 0, D, prec);
+        out_w(g, S.Z(k + 1), prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+    } else {
+      GemmProblem g;  // O = post * Y_{K-1} T_{K-1}
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+      g.alpha_b = post;
+      g.Cf = f32_mat(O, D, D, D, dd);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+  }
+  return EGM_OK;
+}
+
+size_t egm_ns_bwd_workspace(int B, int D, int iters, int prec) {
+  (void)iters; (void)prec;
+  return 6 * pad256(w_bytes(B, D, D)) + pad256((size_t)B * D * D * 4) + 2 * pad256((size_t)B * 4) + 2048;
+}
+
+int egm_ns_bwd(const float* dO, const float* O, const float* M, const float* scal, const void* state,
+               int B, int D, int iters, float eps, int post_mode, float* dM, int prec, void* ws, size_t ws_bytes,
+               egm_stream_t stream) {
+  (void)eps;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_ns_bwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(dO && O && M && scal && state && dM, EGM_ERR_ARG, "egm_ns_bwd: null pointer");
+  EGM_REQUIRE(B > 0 && D > 0 && iters >= 0 && iters <= 64, EGM_ERR_ARG, "egm_ns_bwd: bad sizes");
+  const int K = iters;
+  NsState S(const_cast<void*>(state), B, D, K);
+  Arena ar(ws, ws_bytes);
+  W buf[6];
+  for (int i = 0; i < 6; ++i) buf[i] = make_w(ar.take(w_bytes(B, D, D)), B, D, D);
+  float* dA = static_cast<float*>(ar.take((size_t)B * D * D * 4));
+  float* dotO = static_cast<float*>(ar.take((size_t)B * 4));
+  float* dotA = static_cast<float*>(ar.take((size_t)B * 4));
+  EGM_REQUIRE(buf[5].base && dA && dotO && dotA, EGM_ERR_WORKSPACE, "egm_ns_bwd: workspace %zu < %zu",
+              ws_bytes, egm_ns_bwd_workspace(B, D, iters, prec));
+  const float* inv = scal + B;
+  const float* post = scal + 2 * B;
+  const long long dd = (long long)D * D;
+  // O = post * Y_K :  dY_K = post * dO ;  d tau (through post) = c * <dO,O> / (tau+eps),
+  //   c = -1/2 for post = (tau+eps)^-1/2, +1/2 for post = (tau+eps)^+1/2
+  const float coef_tau = post_mode == 0 ? -0.5f : 0.5f;
+  k::batch_dot(dO, O, B, dd, dotO, st);
+  EGM_LAUNCHED();
+  if (K == 0) {
+    EGM_CUDA(cudaMemsetAsync(dA, 0, (size_t)B * dd * 4, st));
+  } else if (K == 1) {
+    // Y_1 = 1.5 I - 0.5 A : dA = -0.5 * post * dO
+    W dAw;
+    dAw.base = dA; dAw.rows = D; dAw.cols = D; dAw.ld = D; dAw.batch = B;
+    k::affine(dO, D, dd, B, D, D, post, -0.5f, 0.f, dAw, 0.f, 0.f, nullptr, PREC_FP32_SIMT, st);
+    EGM_LAUNCHED();
+  } else {
+    W dY = buf[0], dYn = buf[1], dZ = buf[2], dZn = buf[3], dP = buf[4], X = buf[5];
+    k::affine(dO, D, dd, B, D, D, post, 1.f, 0.f, dY, 0.f, 0.f, nullptr, prec, st);
+    EGM_LAUNCHED();
+    bool have_dZ = false;
+    for (int k = K - 1; k >= 1; --k) {
+      {
+        GemmProblem g;  // dP = -0.5 (Y_k^T dY [+ dZ Z_k^T])
+        g.M = D; g.N = D; g.batch = B;
+        g.t[0] = term(S.Y(k), 1, dY, 0, D, prec);
+        g.nterms = 1;
+        if (have_dZ) { g.t[1] = term(dZ, 0, S.Z(k), 1, D, prec); g.nterms = 2; }
+        g.alpha = -0.5f;
+        out_w(g, dP, prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      {
+        GemmProblem g;  // dY_k = dY T_k^T + Z_k^T dP
+        g.M = D; g.N = D; g.batch = B; g.nterms = 2;
+        g.t[0] = term(dY, 0, S.T(k), 1, D, prec);
+        g.t[1] = term(S.Z(k), 1, dP, 0, D, prec);
+        out_w(g, dYn, prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      {
+        GemmProblem g;  // dZ_k = [T_k^T dZ +] dP Y_k^T
+        g.M = D; g.N = D; g.batch = B;
+        g.t[0] = term(dP, 0, S.Y(k), 1, D, prec);
+        g.nterms = 1;
+        if (have_dZ) { g.t[1] = term(S.T(k), 1, dZ, 0, D, prec); g.nterms = 2; }
+        out_w(g, dZn, prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      W tmp = dY; dY = dYn; dYn = tmp;
+      tmp = dZ; dZ = dZn; dZn = tmp;
+      have_dZ = true;
+    }
+    // k = 0: Y_1 = T_0, Z_1 = T_0 A, T_0 = 1.5 I - 0.5 A
+    {
+      GemmProblem g;  // X = dT_0 = dY_1 + dZ_1 A^T
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(dZ, 0, S.A(), 1, D, prec);
+      addend_w(g, dY, 1.f, prec);
+      out_w(g, X, prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    {
+      GemmProblem g;  // dA = T_0^T dZ_1 - 0.5 dT_0
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(S.T(0), 1, dZ, 0, D, prec);
+      addend_w(g, X, -0.5f, prec);
+      g.Cf = f32_mat(dA, D, D, D, dd);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+  }
+  // A = inv * M with inv = 1/(tau+eps):  dM = inv dA + (d tau) I,
+  //   d tau = coef_tau <dO,O> inv - <dA,M> inv^2
+  k::batch_dot(dA, M, B, dd, dotA, st);
+  k::ns_bwd_finish(dA, inv, dotO, dotA, coef_tau, B, D, dM, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+// ========================================================================== misc
+int egm_triu_pack(const float* O, int B, int D, float* v, egm_stream_t stream) {
+  EGM_REQUIRE(O && v && B > 0 && D > 0, EGM_ERR_ARG, "egm_triu_pack: bad argument");
+  k::triu_pack(O, B, D, v, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_triu_unpack(const float* dv, int B, int D, float* dO, egm_stream_t stream) {
+  EGM_REQUIRE(dv && dO && B > 0 && D > 0, EGM_ERR_ARG, "egm_triu_unpack: bad argument");
+  k::triu_unpack(dv, B, D, dO, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_sketch_fwd(const float* x, int B, int D, int S, const int* off, const int* idx,
+                   const float* sgn, float* cs, float* out, egm_stream_t stream) {
+  EGM_REQUIRE(x && off && idx && sgn && cs && out && B > 0 && D > 0 && S > 0, EGM_ERR_ARG,
+              "egm_sketch_fwd: bad argument");
+  k::sketch_fwd(x, B, D, S, off, idx, sgn, cs, out, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_sketch_bwd(const float* dout, const float* cs, int B, int D, int S, const long long* hash,
+                   const long long* sign, float* dx, egm_stream_t stream) {
+  EGM_REQUIRE(dout && cs && hash && sign && dx && B > 0 && D > 0 && S > 0, EGM_ERR_ARG,
+              "egm_sketch_bwd: bad argument");
+  k::sketch_bwd(dout, cs, B, D, S, hash, sign, dx, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+size_t egm_gram_workspace(int B, int N, int D, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, N, D)) + pad256(w_bytes(B, N, N)) + pad256((size_t)B * N * D * 4) + 1024;
+}
+int egm_gram_fwd(const float* x, int B, int N, int D, int cosine, float eps, float* R, float* nrm,
+                 int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec) && x && R && nrm && B > 0 && N > 0 && D > 0, EGM_ERR_ARG, "egm_gram_fwd: bad argument");
+  Arena ar(ws, ws_bytes);
+  void* wx = ar.take(w_bytes(B, N, D));
+  EGM_REQUIRE(wx, EGM_ERR_WORKSPACE, "egm_gram_fwd: workspace too small");
+  const W Xn = make_w(wx, B, N, D);
+  k::rownorm(x, B, N, D, eps, cosine, nrm, Xn, prec, st);
+  EGM_LAUNCHED();
+  GemmProblem g;
+  g.M = N; g.N = N; g.batch = B; g.nterms = 1;
+  g.t[0] = term(Xn, 0, Xn, 1, D, prec);
+  g.Cf = f32_mat(R, N, N, N, (long long)N * N);
+  EGM_CUDA(run_gemm(g, prec, st));
+  return EGM_OK;
+}
+int egm_gram_bwd(const float* dR, const float* x, const float* nrm, int B, int N, int D, int cosine,
+                 float eps, float* dx, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec) && dR && x && nrm && dx && B > 0 && N > 0 && D > 0, EGM_ERR_ARG, "egm_gram_bwd: bad argument");
+  Arena ar(ws, ws_bytes);
+  void* wx = ar.take(w_bytes(B, N, D));
+  void* wr = ar.take(w_bytes(B, N, N));
+  float* dxn = static_cast<float*>(ar.take((size_t)B * N * D * 4));
+  EGM_REQUIRE(wx && wr && dxn, EGM_ERR_WORKSPACE, "egm_gram_bwd: workspace too small");
+  const W Xn = make_w(wx, B, N, D), dRw = make_w(wr, B, N, N);
+  k::rownorm(x, B, N, D, eps, cosine, dxn, Xn, prec, st);
+  k::affine(dR, N, (long long)N * N, B, N, N, nullptr, 1.f, 0.f, dRw, 0.f, 0.f, nullptr, prec, st);
+  EGM_LAUNCHED();
+  GemmProblem g;  // d Xn = dR Xn + dR^T Xn
+  g.M = N; g.N = D; g.batch = B; g.nterms = 2;
+  g.t[0] = term(dRw, 0, Xn, 0, N, prec);
+  g.t[1] = term(dRw, 1, Xn, 0, N, prec);
+  g.Cf = f32_mat(cosine ? dxn : dx, N, D, D, (long long)N * D);
+  EGM_CUDA(run_gemm(g, prec, st));
+  if (cosine) {
+    k::rownorm_bwd(x, nrm, dxn, B, N, D, eps, dx, st);
+    EGM_LAUNCHED();
+  }
+  return EGM_OK;
+}
+int egm_normalize_graph(const float* G, int B, int N, int method, float eps, float* out, float* deg,
+                        egm_stream_t stream) {
+  EGM_REQUIRE(G && out && deg && B > 0 && N > 0 && (method == 0 || method == 1), EGM_ERR_ARG,
+              "egm_normalize_graph: bad argument");
+  k::normalize_graph(G, B, N, method, eps, out, deg, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_batch_trace(const float* M, int B, int D, float* tr, egm_stream_t stream) {
+  EGM_REQUIRE(M && tr && B > 0 && D > 0, EGM_ERR_ARG, "egm_batch_trace: bad argument");
+  k::batch_trace(M, B, D, tr, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+size_t egm_bmm_workspace(int B, int M, int N, int K, int prec) {
+  (void)prec;
+  return pad256(w_bytes(B, M > K ? M : K, M > K ? M : K)) + pad256(w_bytes(B, N > K ? N : K, N > K ? N : K)) + 1024;
+}
+int egm_bmm(const float* A, int transA, const float* Bm, int transB, int B, int M, int N, int K,
+            float alpha, float* C, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec) && A && Bm && C && B > 0 && M > 0 && N > 0 && K > 0, EGM_ERR_ARG, "egm_bmm: bad argument");
+  const int ar_ = transA ? K : M, ac = transA ? M : K, br = transB ? N : K, bc = transB ? K : N;
+  Arena ar(ws, ws_bytes);
+  void* wa = ar.take(w_bytes(B, ar_, ac));
+  void* wb = ar.take(w_bytes(B, br, bc));
+  EGM_REQUIRE(wa && wb, EGM_ERR_WORKSPACE, "egm_bmm: workspace too small");
+  const W Aw = make_w(wa, B, ar_, ac), Bw = make_w(wb, B, br, bc);
+  k::affine(A, ac, (long long)ar_ * ac, B, ar_, ac, nullptr, 1.f, 0.f, Aw, 0.f, 0.f, nullptr, prec, st);
+  k::affine(Bm, bc, (long long)br * bc, B, br, bc, nullptr, 1.f, 0.f, Bw, 0.f, 0.f, nullptr, prec, st);
+  EGM_LAUNCHED();
+  GemmProblem g;
+  g.M = M; g.N = N; g.batch = B; g.nterms = 1;
+  g.t[0] = term(Aw, transA, Bw, transB, K, prec);
+  g.alpha = alpha;
+  g.Cf = f32_mat(C, M, N, N, (long long)M * N);
+  EGM_CUDA(run_gemm(g, prec, st));
+  return EGM_OK;
+}
+
+}  // extern "C"

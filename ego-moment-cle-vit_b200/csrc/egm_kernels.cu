@@ -1,0 +1,734 @@
+// Definitions of the bandwidth-bound kernels declared in egm_kernels.cuh.
+// Reference arithmetic being reproduced (all fp32):
+//   src/models/gpf_kernel.py:75-115,133-157   normalise / Hadamard powers / symmetrise / clamp
+//   src/models/moment_head.py:222-266         degree normalisation, graph-weighted mean
+//   src/models/moment_head.py:42-45,67-68     trace pre-normalisation / post-compensation
+//   src/models/moment_head.py:100-131         count sketch x3 and their product
+//   src/models/moment_head.py:215-218         triu half-vectorisation (row-major order)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "egm_kernels.cuh"
+
+namespace egm {
+namespace k {
+namespace {
+
+constexpr int kMaxDeg = 15;  // Hadamard powers 0..15 per view
+
+struct WPtr {
+  float* f;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  long long ld, bs;
+};
+WPtr wptr(const W& w, int prec) {
+  WPtr p = {};
+  p.ld = w.ld;
+  p.bs = (long long)w.rows * w.ld;
+  if (prec == PREC_FP32_SIMT) {
+    p.f = static_cast<float*>(w.base);
+  } else {
+    p.hi = static_cast<__nv_bfloat16*>(w.base);
+    p.lo = (prec == PREC_BF16X3) ? p.hi + (long long)w.batch * w.rows * w.ld : nullptr;
+  }
+  return p;
+}
+__device__ __forceinline__ void wstore(const WPtr& p, long long off, float x) {
+  if (p.f) {
+    p.f[off] = x;
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    p.hi[off] = h;
+    if (p.lo) p.lo[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+__device__ __forceinline__ void wstore4(const WPtr& p, long long off, float4 x) {
+  if (p.f) {
+    *reinterpret_cast<float4*>(p.f + off) = x;
+  } else {
+    const float v[4] = {x.x, x.y, x.z, x.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __float2bfloat16_rn(v[i]);
+      l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i]));
+    }
+    uint2 hh, ll;
+    hh.x = __bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    hh.y = __bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    *reinterpret_cast<uint2*>(p.hi + off) = hh;
+    if (p.lo) {
+      ll.x = __bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+      ll.y = __bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+      *reinterpret_cast<uint2*>(p.lo + off) = ll;
+    }
+  }
+}
+__device__ __forceinline__ float wload(const WPtr& p, long long off) {
+  if (p.f) return p.f[off];
+  float x = __bfloat162float(p.hi[off]);
+  if (p.lo) x += __bfloat162float(p.lo[off]);
+  return x;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum, result valid in every thread; `sh` needs 32 floats
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (wid == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  return sh[0];
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------- affine
+template <int V>
+__global__ void affine_kernel(const float* __restrict__ x, long long ld, long long bs, int rows,
+                              int cols, const float* __restrict__ s, float a1, float b1, WPtr o1,
+                              float a2, float b2, WPtr o2, int has2) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (j >= cols) return;
+  const float sc = s ? s[b] : 1.f;
+  const float* src = x + (long long)b * bs + (long long)i * ld + j;
+  if (V == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src);
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float r1[4], r2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float e = (i == j + q) ? 1.f : 0.f;
+      r1[q] = a1 * sc * in[q] + b1 * e;
+      r2[q] = a2 * sc * in[q] + b2 * e;
+    }
+    wstore4(o1, (long long)b * o1.bs + (long long)i * o1.ld + j, make_float4(r1[0], r1[1], r1[2], r1[3]));
+    if (has2) wstore4(o2, (long long)b * o2.bs + (long long)i * o2.ld + j, make_float4(r2[0], r2[1], r2[2], r2[3]));
+  } else {
+    const float e = (i == j) ? 1.f : 0.f;
+    const float v = *src;
+    wstore(o1, (long long)b * o1.bs + (long long)i * o1.ld + j, a1 * sc * v + b1 * e);
+    if (has2) wstore(o2, (long long)b * o2.bs + (long long)i * o2.ld + j, a2 * sc * v + b2 * e);
+  }
+}
+
+template <int V>
+__global__ void export_kernel(WPtr in, int rows, int cols, float* __restrict__ out, long long ld,
+                              long long bs) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  out[(long long)b * bs + (long long)i * ld + j] = wload(in, (long long)b * in.bs + (long long)i * in.ld + j);
+}
+
+// ------------------------------------------------------------------ rownorm
+__global__ void rownorm_kernel(const float* __restrict__ x, int n, int d, float eps, int cosine,
+                               float* __restrict__ nrm, WPtr xn) {
+  // one warp per token row
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = x + ((long long)b * n + row) * d;
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) { const float v = src[j]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float nr = sqrtf(ss);
+  if (lane == 0) nrm[(long long)b * n + row] = nr;
+  const float inv = cosine ? 1.f / fmaxf(nr, eps) : 1.f;
+  const long long o = (long long)b * xn.bs + (long long)row * xn.ld;
+  for (int j = lane; j < d; j += 32) wstore(xn, o + j, src[j] * inv);
+}
+
+__global__ void rownorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ nrm,
+                                   const float* __restrict__ dxn, int n, int d, float eps,
+                                   float* __restrict__ dx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const long long o = ((long long)b * n + row) * d;
+  const float nr = nrm[(long long)b * n + row];
+  if (nr >= eps) {
+    // F.normalize: x / clamp_min(||x||, eps); the clamp passes gradient when ||x|| >= eps
+    const float inv = 1.f / nr;
+    float dot = 0.f;
+    for (int j = lane; j < d; j += 32) dot = fmaf(x[o + j] * inv, dxn[o + j], dot);
+    dot = warp_sum(dot);
+    for (int j = lane; j < d; j += 32) dx[o + j] = (dxn[o + j] - x[o + j] * inv * dot) * inv;
+  } else {
+    const float inv = 1.f / eps;
+    for (int j = lane; j < d; j += 32) dx[o + j] = dxn[o + j] * inv;
+  }
+}
+
+// --------------------------------------------------------------- polynomial
+__device__ __forceinline__ void had_powers(float x, int deg, float* pw) {
+  // f_0 = 1, f_1 = x (NOT clamped), f_k = max(x,0)^k   (gpf_kernel.py:107-115)
+  pw[0] = 1.f;
+  if (deg >= 1) pw[1] = x;
+  const float c = fmaxf(x, 0.f);
+  float acc = c;
+  for (int k = 2; k <= deg; ++k) { acc *= c; pw[k] = acc; }
+}
+__device__ __forceinline__ void had_dpowers(float x, int deg, float* dp) {
+  // f'_0 = 0, f'_1 = 1, f'_k = k max(x,0)^(k-1)
+  dp[0] = 0.f;
+  if (deg >= 1) dp[1] = 1.f;
+  const float c = fmaxf(x, 0.f);
+  float acc = 1.f;
+  for (int k = 2; k <= deg; ++k) { acc *= c; dp[k] = k * acc; }
+}
+__device__ __forceinline__ float poly_eval(const float* pa, const float* pb, const float* coef, int P, int Q) {
+  float f = 0.f;
+  for (int p = 0; p <= P; ++p) {
+    float inner = 0.f;
+    for (int q = 0; q <= Q; ++q) inner = fmaf(coef[p * (Q + 1) + q], pb[q], inner);
+    f = fmaf(pa[p], inner, f);
+  }
+  return f;
+}
+
+__global__ void gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
+                                    long long ldR, const float* __restrict__ coef, int P, int Q,
+                                    int symmetric, int n, float* __restrict__ G) {
+  __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
+  for (int t = threadIdx.x; t < (P + 1) * (Q + 1); t += blockDim.x) c[t] = coef[t];
+  __syncthreads();
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long base = (long long)b * n * ldR;
+  float pa[kMaxDeg + 1], pb[kMaxDeg + 1];
+  had_powers(Ra[base + (long long)i * ldR + j], P, pa);
+  had_powers(Rp[base + (long long)i * ldR + j], Q, pb);
+  float f = poly_eval(pa, pb, c, P, Q);
+  if (symmetric) {
+    had_powers(Ra[base + (long long)j * ldR + i], P, pa);
+    had_powers(Rp[base + (long long)j * ldR + i], Q, pb);
+    const float ft = poly_eval(pa, pb, c, P, Q);
+    f = 0.5f * (f + ft);
+  }
+  G[((long long)b * n + i) * n + j] = fmaxf(f, 0.f);
+}
+
+// one block handles a strip of rows of one image; deterministic two-stage dcoef reduction
+constexpr int kPolyBwdRows = 8;
+__global__ void __launch_bounds__(256)
+gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
+                    const float* __restrict__ Rp, long long ldR, const float* __restrict__ coef,
+                    int P, int Q, int symmetric, int n, WPtr Ea, WPtr Ep,
+                    float* __restrict__ partial) {
+  __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
+  __shared__ float red[(kMaxDeg + 1) * (kMaxDeg + 1)];
+  __shared__ float sh[32];
+  const int nt = (P + 1) * (Q + 1);
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) { c[t] = coef[t]; red[t] = 0.f; }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * kPolyBwdRows;
+  const long long rb = (long long)b * n * ldR;
+  const long long gb = (long long)b * n * n;
+  // small-degree fast path keeps the per-term sums in registers
+  float acc[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+  for (int e = threadIdx.x; e < kPolyBwdRows * n; e += blockDim.x) {
+    const int i = i0 + e / n, j = e % n;
+    if (i >= n) break;
+    float pa[kMaxDeg + 1], pb[kMaxDeg + 1], pat[kMaxDeg + 1], pbt[kMaxDeg + 1];
+    const float ra = Ra[rb + (long long)i * ldR + j], rp = Rp[rb + (long long)i * ldR + j];
+    const float rat = Ra[rb + (long long)j * ldR + i], rpt = Rp[rb + (long long)j * ldR + i];
+    had_powers(ra, P, pa); had_powers(rp, Q, pb);
+    had_powers(rat, P, pat); had_powers(rpt, Q, pbt);
+    const float f = poly_eval(pa, pb, c, P, Q), ft = poly_eval(pat, pbt, c, P, Q);
+    const float g_ij = dG[gb + (long long)i * n + j], g_ji = dG[gb + (long long)j * n + i];
+    float dF_ij, dF_ji;
+    if (symmetric) {
+      const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
+      dF_ij = dF_ji = 0.5f * (g_ij + g_ji) * sgate;
+    } else {
+      dF_ij = (f >= 0.f) ? g_ij : 0.f;
+      dF_ji = (ft >= 0.f) ? g_ji : 0.f;
+    }
+    // dRa_ij + dRa_ji  and  dRp_ij + dRp_ji
+    float da[kMaxDeg + 1], db[kMaxDeg + 1], dat[kMaxDeg + 1], dbt[kMaxDeg + 1];
+    had_dpowers(ra, P, da); had_dpowers(rp, Q, db);
+    had_dpowers(rat, P, dat); had_dpowers(rpt, Q, dbt);
+    const float ea = dF_ij * poly_eval(da, pb, c, P, Q) + dF_ji * poly_eval(dat, pbt, c, P, Q);
+    const float ep = dF_ij * poly_eval(pa, db, c, P, Q) + dF_ji * poly_eval(pat, dbt, c, P, Q);
+    wstore(Ea, (long long)b * Ea.bs + (long long)i * Ea.ld + j, ea);
+    wstore(Ep, (long long)b * Ep.bs + (long long)i * Ep.ld + j, ep);
+    if (nt <= 16) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < nt) acc[t] = fmaf(dF_ij, pa[t / (Q + 1)] * pb[t % (Q + 1)], acc[t]);
+    } else {
+      for (int t = 0; t < nt; ++t) atomicAdd(&red[t], dF_ij * pa[t / (Q + 1)] * pb[t % (Q + 1)]);
+    }
+  }
+  float* out = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * nt;
+  if (nt <= 16) {
+    for (int t = 0; t < nt; ++t) {
+      const float v = block_sum(acc[t], sh);
+      if (threadIdx.x == 0) out[t] = v;
+    }
+  } else {
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) out[t] = red[t];
+  }
+}
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int nt,
+                                       float* __restrict__ out) {
+  __shared__ float sh[32];
+  const int t = blockIdx.x;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) a += partial[(long long)i * nt + t];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) out[t] = a;
+}
+
+// ---------------------------------------------------------- degree / weight
+__global__ void degree_kernel(const float* __restrict__ G, int n, float eps, float* __restrict__ deg,
+                              float* __restrict__ s) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* g = G + ((long long)b * n + row) * n;
+  float a = 0.f;
+  for (int j = lane; j < n; j += 32) a += g[j];
+  a = warp_sum(a);
+  if (lane == 0) {
+    deg[(long long)b * n + row] = a;
+    s[(long long)b * n + row] = rsqrtf(fmaxf(a, eps));
+  }
+}
+__global__ void weight_kernel(const float* __restrict__ G, const float* __restrict__ s, int n,
+                              WPtr Wn, float* __restrict__ w, float* __restrict__ wdiag) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* g = G + ((long long)b * n + row) * n;
+  const float* sb = s + (long long)b * n;
+  const float si = sb[row];
+  float a = 0.f;
+  const long long o = (long long)b * Wn.bs + (long long)row * Wn.ld;
+  for (int j = lane; j < n; j += 32) {
+    const float v = g[j] * si * sb[j];   // graph * s_i * s_j, same association as the reference
+    a += v;
+    wstore(Wn, o + j, v);
+    if (j == row) wdiag[(long long)b * n + row] = v;
+  }
+  a = warp_sum(a);
+  if (lane == 0) w[(long long)b * n + row] = a;
+}
+
+// ------------------------------------------------------------- mean / centre
+__global__ void __launch_bounds__(128)
+mean_center_kernel(const float* __restrict__ Z, const float* __restrict__ w,
+                   const float* __restrict__ wdiag, int n, int d, float eps, float* __restrict__ t_out,
+                   float* __restrict__ sw_out, float* __restrict__ mu, float* __restrict__ u, WPtr Zc) {
+  extern __shared__ float shw[];  // n weights
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  float tl = 0.f, sl = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float wi = w[(long long)b * n + i];
+    shw[i] = wi;
+    sl += wi;
+    tl += wdiag[(long long)b * n + i];
+  }
+  const float t = block_sum(tl, sh);
+  const float sw = block_sum(sl, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { t_out[b] = t; sw_out[b] = sw; }
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const float* z = Z + (long long)b * n * d + j;
+  float a = 0.f;
+  for (int i = 0; i < n; ++i) a = fmaf(shw[i], z[(long long)i * d], a);
+  const float inv = 1.f / (t + eps);
+  const float m = a * inv;
+  mu[(long long)b * d + j] = m;
+  float ua = 0.f;
+  const long long o = (long long)b * Zc.bs + j;
+  for (int i = 0; i < n; ++i) {
+    const float zc = z[(long long)i * d] - m;
+    ua = fmaf(zc, shw[i], ua);
+    wstore(Zc, o + (long long)i * Zc.ld, zc);
+  }
+  if (u) u[(long long)b * d + j] = ua * inv;
+}
+
+// ------------------------------------------------------------ trace, dots
+__global__ void trace_scales_kernel(const float* __restrict__ M, int d, float eps, int post_mode,
+                                    float* __restrict__ tr, float* __restrict__ inv,
+                                    float* __restrict__ post) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* m = M + (long long)b * d * d;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) a += m[(long long)i * d + i];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) {
+    tr[b] = a;
+    inv[b] = 1.f / (a + eps);
+    const float r = sqrtf(a + eps);
+    post[b] = post_mode == 0 ? 1.f / r : r;
+  }
+}
+__global__ void batch_dot_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                 long long n_per, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const float* x = X + (long long)b * n_per;
+  const float* y = Y + (long long)b * n_per;
+  float a = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per;
+       i += (long long)gridDim.x * blockDim.x)
+    a = fmaf(x[i], y[i], a);
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) partial[(long long)b * gridDim.x + blockIdx.x] = a;
+}
+__global__ void ns_bwd_finish_kernel(const float* __restrict__ dA, const float* __restrict__ inv,
+                                     const float* __restrict__ dotO, const float* __restrict__ dotA,
+                                     float coef_tau, int d, float* __restrict__ dM) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const long long o = ((long long)b * d + i) * d + j;
+  float v = dA[o] * inv[b];
+  if (i == j) v += (coef_tau * dotO[b] - dotA[b] * inv[b]) * inv[b];
+  dM[o] = v;
+}
+
+__global__ void clamped_degree_kernel(const float* __restrict__ G, int n, float eps,
+                                      float* __restrict__ deg) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* g = G + ((long long)b * n + row) * n;
+  float a = 0.f;
+  for (int j = lane; j < n; j += 32) a += g[j];
+  a = warp_sum(a);
+  if (lane == 0) deg[(long long)b * n + row] = fmaxf(a, eps);
+}
+__global__ void normalize_graph_kernel(const float* __restrict__ G, const float* __restrict__ deg,
+                                       int n, int method, float* __restrict__ out) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long o = ((long long)b * n + i) * n + j;
+  const float di = deg[(long long)b * n + i];
+  if (method == 0) {
+    const float ii = 1.f / sqrtf(di), ij = 1.f / sqrtf(deg[(long long)b * n + j]);
+    out[o] = G[o] * ii * ij;
+  } else {
+    out[o] = G[o] * (1.f / di);
+  }
+}
+__global__ void batch_trace_kernel(const float* __restrict__ M, int d, float* __restrict__ tr) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float* m = M + (long long)b * d * d;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) a += m[(long long)i * d + i];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) tr[b] = a;
+}
+
+// ------------------------------------------------------------------- triu
+__global__ void triu_pack_kernel(const float* __restrict__ O, int d, float* __restrict__ v) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d || j < i) return;
+  const long long L = (long long)d * (d + 1) / 2;
+  const long long off = (long long)i * d - (long long)i * (i - 1) / 2 + (j - i);
+  v[(long long)b * L + off] = O[((long long)b * d + i) * d + j];
+}
+__global__ void triu_unpack_kernel(const float* __restrict__ dv, int d, float* __restrict__ dO) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const long long L = (long long)d * (d + 1) / 2;
+  float x = 0.f;
+  if (j >= i) x = dv[(long long)b * L + (long long)i * d - (long long)i * (i - 1) / 2 + (j - i)];
+  dO[((long long)b * d + i) * d + j] = x;
+}
+
+// ----------------------------------------------------------------- sketch
+__global__ void sketch_fwd_kernel(const float* __restrict__ x, int batch, int d, int S,
+                                  const int* __restrict__ off, const int* __restrict__ idx,
+                                  const float* __restrict__ sgn, float* __restrict__ cs,
+                                  float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float* xb = x + (long long)b * d;
+  float prod = 1.f;
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const int* o = off + (long long)h * (S + 1);
+    float a = 0.f;
+    for (int e = o[s]; e < o[s + 1]; ++e) a += sgn[h * d + e] * xb[idx[h * d + e]];
+    cs[((long long)h * batch + b) * S + s] = a;
+    prod *= a;
+  }
+  out[(long long)b * S + s] = prod;
+}
+__global__ void sketch_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ cs,
+                                  int batch, int d, int S, const long long* __restrict__ hash,
+                                  const long long* __restrict__ sign, float* __restrict__ dx) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  float a = 0.f;
+#pragma unroll
+  for (int h = 0; h < 3; ++h) {
+    const long long s = hash[(long long)h * d + j];
+    float others = 1.f;
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+      if (g != h) others *= cs[((long long)g * batch + b) * S + s];
+    a += static_cast<float>(sign[(long long)h * d + j]) * dout[(long long)b * S + s] * others;
+  }
+  dx[(long long)b * d + j] = a;
+}
+
+// ---------------------------------------------------------- pooling backward
+__global__ void __launch_bounds__(128)
+pool_bwd_dmu_kernel(const float* __restrict__ dZc, const float* __restrict__ du,
+                    const float* __restrict__ sw, const float* __restrict__ t, int n, int d,
+                    float eps, float* __restrict__ dmu) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const float* p = dZc + (long long)b * n * d + j;
+  float a = 0.f;
+  for (int i = 0; i < n; ++i) a += p[(long long)i * d];
+  if (du) a += sw[b] * du[(long long)b * d + j] / (t[b] + eps);
+  dmu[(long long)b * d + j] = -a;
+}
+__global__ void pool_bwd_rows_kernel(const float* __restrict__ dZc, const float* __restrict__ Z,
+                                     WPtr Zc, const float* __restrict__ w, const float* __restrict__ t,
+                                     const float* __restrict__ mu, const float* __restrict__ u,
+                                     const float* __restrict__ du, const float* __restrict__ dmu,
+                                     int n, int d, float eps, float* __restrict__ dZ,
+                                     float* __restrict__ dw, float* __restrict__ dt) {
+  // one warp per token row; block (0, b) additionally reduces dt
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const float inv = 1.f / (t[b] + eps);
+  const float* dmub = dmu + (long long)b * d;
+  const float* dub = du ? du + (long long)b * d : nullptr;
+  if (row < n) {
+    const float wi = w[(long long)b * n + row] * inv;
+    const long long o = ((long long)b * n + row) * d;
+    const long long oc = (long long)b * Zc.bs + (long long)row * Zc.ld;
+    float a = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float dmj = dmub[j];
+      const float duj = dub ? dub[j] : 0.f;
+      dZ[o + j] = dZc[o + j] + wi * (duj + dmj);
+      a = fmaf(Z[o + j], dmj, a);
+      if (dub) a = fmaf(wload(Zc, oc + j), duj, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) dw[(long long)b * n + row] = a * inv;
+  }
+  if (blockIdx.x == 0 && (threadIdx.x >> 5) == 0) {
+    float a = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      a = fmaf(mu[(long long)b * d + j], dmub[j], a);
+      if (dub) a = fmaf(u[(long long)b * d + j], dub[j], a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) dt[b] = -a * inv;
+  }
+}
+__global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
+                                   const float* __restrict__ dw, const float* __restrict__ dt,
+                                   const float* __restrict__ G, const float* __restrict__ s, int n,
+                                   float* __restrict__ ds) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* dWb = dW + (long long)b * n * ldW;
+  const float* Gb = G + (long long)b * n * n;
+  const float* sb = s + (long long)b * n;
+  const float* dwb = dw + (long long)b * n;
+  const float dtb = dt[b];
+  const int i = row;
+  float a = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float dij = dWb[(long long)i * ldW + j] + dwb[i] + (i == j ? dtb : 0.f);
+    const float dji = dWb[(long long)j * ldW + i] + dwb[j] + (i == j ? dtb : 0.f);
+    a += (dij * Gb[(long long)i * n + j] + dji * Gb[(long long)j * n + i]) * sb[j];
+  }
+  a = warp_sum(a);
+  if (lane == 0) ds[(long long)b * n + i] = a;
+}
+__global__ void pool_bwd_dG_kernel(const float* __restrict__ dW, long long ldW,
+                                   const float* __restrict__ dw, const float* __restrict__ dt,
+                                   const float* __restrict__ s, const float* __restrict__ deg,
+                                   const float* __restrict__ ds, int n, float eps,
+                                   float* __restrict__ dG) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float si = s[(long long)b * n + i], sj = s[(long long)b * n + j];
+  const float dwf = dW[((long long)b * n + i) * ldW + j] + dw[(long long)b * n + i] + (i == j ? dt[b] : 0.f);
+  // s = max(deg,eps)^(-1/2): d s/d deg = -0.5 s^3 where the clamp is inactive (deg >= eps)
+  const float ddeg = (deg[(long long)b * n + i] >= eps) ? -0.5f * si * si * si * ds[(long long)b * n + i] : 0.f;
+  dG[((long long)b * n + i) * n + j] = si * dwf * sj + ddeg;
+}
+
+}  // namespace
+
+// ================================================================ launchers
+void affine(const float* x, long long ld, long long bs, int batch, int rows, int cols,
+            const float* s, float a1, float b1, const W& out1, float a2, float b2, const W* out2,
+            int prec, cudaStream_t st) {
+  WPtr o1 = wptr(out1, prec), o2 = out2 ? wptr(*out2, prec) : WPtr{};
+  const bool vec = (cols % 4 == 0) && (ld % 4 == 0) && (bs % 4 == 0) && aligned16(x) && aligned16(out1.base) &&
+                   (!out2 || aligned16(out2->base));
+  if (vec) {
+    dim3 grid((cols / 4 + 127) / 128, rows, batch);
+    affine_kernel<4><<<grid, 128, 0, st>>>(x, ld, bs, rows, cols, s, a1, b1, o1, a2, b2, o2, out2 != nullptr);
+  } else {
+    dim3 grid((cols + 127) / 128, rows, batch);
+    affine_kernel<1><<<grid, 128, 0, st>>>(x, ld, bs, rows, cols, s, a1, b1, o1, a2, b2, o2, out2 != nullptr);
+  }
+}
+void export_f32(const W& in, float* out, long long ld, long long bs, int prec, cudaStream_t st) {
+  dim3 grid((in.cols + 127) / 128, in.rows, in.batch);
+  export_kernel<1><<<grid, 128, 0, st>>>(wptr(in, prec), in.rows, in.cols, out, ld, bs);
+}
+void rownorm(const float* x, int batch, int n, int d, float eps, int cosine, float* nrm, const W& xn,
+             int prec, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  rownorm_kernel<<<grid, 256, 0, st>>>(x, n, d, eps, cosine, nrm, wptr(xn, prec));
+}
+void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, int n, int d,
+                 float eps, float* dx, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  rownorm_bwd_kernel<<<grid, 256, 0, st>>>(x, nrm, dxn, n, d, eps, dx);
+}
+void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
+                  int symmetric, int batch, int n, float* G, cudaStream_t st) {
+  dim3 grid((n + 127) / 128, n, batch);
+  gpf_poly_fwd_kernel<<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+}
+int gpf_poly_bwd_blocks(int batch, int n) { return batch * ((n + kPolyBwdRows - 1) / kPolyBwdRows); }
+void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
+                  const float* coef, int P, int Q, int symmetric, int batch, int n, const W& Ea,
+                  const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
+                  cudaStream_t st) {
+  dim3 grid((n + kPolyBwdRows - 1) / kPolyBwdRows, batch);
+  gpf_poly_bwd_kernel<<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
+                                            wptr(Ep, prec), partial);
+  const int nt = (P + 1) * (Q + 1);
+  reduce_partials_kernel<<<nt, 256, 0, st>>>(partial, nblocks, nt, dcoef);
+}
+void degree(const float* G, int batch, int n, float eps, float* deg, float* s, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  degree_kernel<<<grid, 256, 0, st>>>(G, n, eps, deg, s);
+}
+void weight(const float* G, const float* s, int batch, int n, const W& Wn, float* w, float* wdiag,
+            int prec, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  weight_kernel<<<grid, 256, 0, st>>>(G, s, n, wptr(Wn, prec), w, wdiag);
+}
+void mean_center(const float* Z, const float* w, const float* wdiag, int batch, int n, int d,
+                 float eps, float* t, float* sw, float* mu, float* u, const W& Zc, int prec,
+                 cudaStream_t st) {
+  dim3 grid((d + 127) / 128, batch);
+  mean_center_kernel<<<grid, 128, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu, u,
+                                                           wptr(Zc, prec));
+}
+void trace_scales(const float* M, int batch, int d, float eps, int post_mode, float* tr, float* inv,
+                  float* post, cudaStream_t st) {
+  trace_scales_kernel<<<batch, 256, 0, st>>>(M, d, eps, post_mode, tr, inv, post);
+}
+void batch_dot(const float* X, const float* Y, int batch, long long n_per, float* out,
+               cudaStream_t st) {
+  // single deterministic block per image (grid.x = 1): n_per is at most ~1M elements
+  dim3 grid(1, batch);
+  batch_dot_kernel<<<grid, 1024, 0, st>>>(X, Y, n_per, out);
+}
+void ns_bwd_finish(const float* dA, const float* inv, const float* dotO, const float* dotA,
+                   float coef_tau, int batch, int d, float* dM, cudaStream_t st) {
+  dim3 grid((d + 127) / 128, d, batch);
+  ns_bwd_finish_kernel<<<grid, 128, 0, st>>>(dA, inv, dotO, dotA, coef_tau, d, dM);
+}
+void normalize_graph(const float* G, int batch, int n, int method, float eps, float* out,
+                     float* deg, cudaStream_t st) {
+  dim3 g1((n + 7) / 8, batch);
+  clamped_degree_kernel<<<g1, 256, 0, st>>>(G, n, eps, deg);
+  dim3 g2((n + 127) / 128, n, batch);
+  normalize_graph_kernel<<<g2, 128, 0, st>>>(G, deg, n, method, out);
+}
+void batch_trace(const float* M, int batch, int d, float* tr, cudaStream_t st) {
+  batch_trace_kernel<<<batch, 256, 0, st>>>(M, d, tr);
+}
+void triu_pack(const float* O, int batch, int d, float* v, cudaStream_t st) {
+  dim3 grid((d + 127) / 128, d, batch);
+  triu_pack_kernel<<<grid, 128, 0, st>>>(O, d, v);
+}
+void triu_unpack(const float* dv, int batch, int d, float* dO, cudaStream_t st) {
+  dim3 grid((d + 127) / 128, d, batch);
+  triu_unpack_kernel<<<grid, 128, 0, st>>>(dv, d, dO);
+}
+void sketch_fwd(const float* x, int batch, int d, int S, const int* off, const int* idx,
+                const float* sgn, float* cs, float* out, cudaStream_t st) {
+  dim3 grid((S + 255) / 256, batch);
+  sketch_fwd_kernel<<<grid, 256, 0, st>>>(x, batch, d, S, off, idx, sgn, cs, out);
+}
+void sketch_bwd(const float* dout, const float* cs, int batch, int d, int S, const long long* hash,
+                const long long* sign, float* dx, cudaStream_t st) {
+  dim3 grid((d + 255) / 256, batch);
+  sketch_bwd_kernel<<<grid, 256, 0, st>>>(dout, cs, batch, d, S, hash, sign, dx);
+}
+void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,
+                  int n, int d, float eps, float* dmu, cudaStream_t st) {
+  dim3 grid((d + 127) / 128, batch);
+  pool_bwd_dmu_kernel<<<grid, 128, 0, st>>>(dZc, du, sw, t, n, d, eps, dmu);
+}
+void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w, const float* t,
+                   const float* mu, const float* u, const float* du, const float* dmu, int batch,
+                   int n, int d, float eps, float* dZ, float* dw, float* dt, int prec,
+                   cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  pool_bwd_rows_kernel<<<grid, 256, 0, st>>>(dZc, Z, wptr(Zc, prec), w, t, mu, u, du, dmu, n, d, eps,
+                                             dZ, dw, dt);
+}
+void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* dt, const float* G,
+                 const float* s, int batch, int n, float* ds, cudaStream_t st) {
+  dim3 grid((n + 7) / 8, batch);
+  pool_bwd_ds_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, G, s, n, ds);
+}
+void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
+                 const float* deg, const float* ds, int batch, int n, float eps, float* dG,
+                 cudaStream_t st) {
+  dim3 grid((n + 127) / 128, n, batch);
+  pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, dG);
+}
+
+}  // namespace k
+}  // namespace egm

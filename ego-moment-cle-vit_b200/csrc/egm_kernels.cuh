@@ -1,0 +1,125 @@
+// Bandwidth-bound kernels of the moment-pooling path (everything that is not a GEMM):
+// token normalisation, Hadamard-power polynomial + symmetrise + clamp, degree
+// normalisation, graph-weighted mean / centring, trace, triu pack, count-sketch, and the
+// matching backward passes. Launchers only; definitions in egm_kernels.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "egm_gemm.h"
+
+namespace egm {
+
+// A "working matrix": batched row-major [batch][rows][ld] in the native operand format of
+// the active precision mode - fp32 (PREC_FP32_SIMT) or bf16 hi/lo planes (tensor-core
+// modes; the lo plane sits `batch*rows*ld` bf16 elements after the hi plane).
+struct W {
+  void* base = nullptr;
+  int rows = 0, cols = 0;
+  long long ld = 0;
+  int batch = 1;
+};
+inline long long w_ld(int cols) { return ((long long)cols + 7) / 8 * 8; }
+inline size_t w_bytes(int batch, int rows, int cols) {
+  return (size_t)batch * rows * w_ld(cols) * 4;
+}
+inline W make_w(void* base, int batch, int rows, int cols) {
+  W w;
+  w.base = base; w.rows = rows; w.cols = cols; w.ld = w_ld(cols); w.batch = batch;
+  return w;
+}
+// View of a working matrix as a GEMM operand.
+inline Mat w_mat(const W& w, int prec) {
+  Mat m;
+  m.p0 = w.base;
+  m.rows = w.rows; m.cols = w.cols; m.ld = w.ld; m.bstride = (long long)w.rows * w.ld;
+  if (prec == PREC_BF16X3)
+    m.p1 = static_cast<__nv_bfloat16*>(w.base) + (long long)w.batch * w.rows * w.ld;
+  return m;
+}
+inline Mat f32_mat(const void* p, int rows, int cols, long long ld, long long bstride) {
+  Mat m;
+  m.p0 = const_cast<void*>(p); m.rows = rows; m.cols = cols; m.ld = ld; m.bstride = bstride;
+  return m;
+}
+
+namespace k {
+
+// out_i = a_i * s[b] * x + b_i * I  for i in {1,2}  (out2 optional; s optional)
+void affine(const float* x, long long ld, long long bs, int batch, int rows, int cols,
+            const float* s, float a1, float b1, const W& out1, float a2, float b2, const W* out2,
+            int prec, cudaStream_t st);
+// working matrix -> fp32
+void export_f32(const W& in, float* out, long long ld, long long bs, int prec, cudaStream_t st);
+
+// nrm[b,i] = ||x_i||;  xn = x / max(nrm, eps) (cosine) or x (dot)  -> working matrix
+void rownorm(const float* x, int batch, int n, int d, float eps, int cosine, float* nrm,
+             const W& xn, int prec, cudaStream_t st);
+// da = (dAn - An*(An.dAn)) / max(nrm,eps)  [nrm >= eps]  else dAn/eps
+void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, int n, int d,
+                 float eps, float* dx, cudaStream_t st);
+
+// G = max(sym(sum_pq c_pq f_p(Ra) f_q(Rp)), 0)
+void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
+                  int symmetric, int batch, int n, float* G, cudaStream_t st);
+// Ea = dRa + dRa^T, Ep = dRp + dRp^T (working matrices), dcoef[(P+1)(Q+1)]
+void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
+                  const float* coef, int P, int Q, int symmetric, int batch, int n, const W& Ea,
+                  const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
+                  cudaStream_t st);
+int gpf_poly_bwd_blocks(int batch, int n);
+
+// deg = G 1 ; s = rsqrt(max(deg, eps))
+void degree(const float* G, int batch, int n, float eps, float* deg, float* s, cudaStream_t st);
+// Wn_ij = s_i G_ij s_j (working matrix) ; w = Wn 1 ; wdiag_i = Wn_ii
+void weight(const float* G, const float* s, int batch, int n, const W& Wn, float* w, float* wdiag,
+            int prec, cudaStream_t st);
+// t = sum wdiag ; sw = sum w ; mu = Z^T w/(t+eps) ; Zc = Z - mu ; u = Zc^T w /(t+eps)
+void mean_center(const float* Z, const float* w, const float* wdiag, int batch, int n, int d,
+                 float eps, float* t, float* sw, float* mu, float* u, const W& Zc, int prec,
+                 cudaStream_t st);
+
+// tr = trace(M); inv = 1/(tr+eps); post = (tr+eps)^(-1/2) [mode 0] or (tr+eps)^(1/2) [mode 1]
+void trace_scales(const float* M, int batch, int d, float eps, int post_mode, float* tr,
+                  float* inv, float* post, cudaStream_t st);
+// out[b] = <X[b], Y[b]>  (fp32 matrices, same layout)
+void batch_dot(const float* X, const float* Y, int batch, long long n_per, float* out,
+               cudaStream_t st);
+// dM = dA*inv + (coef_tau*dotO - dotA*inv)*inv I   with dotO = <dO,O>, dotA = <dA,M>
+void ns_bwd_finish(const float* dA, const float* inv, const float* dotO, const float* dotA,
+                   float coef_tau, int batch, int d, float* dM, cudaStream_t st);
+
+// utils.ops.normalize_graph: deg = max(G 1, eps); method 0: G_ij/sqrt(deg_i deg_j); 1: G_ij/deg_i
+void normalize_graph(const float* G, int batch, int n, int method, float eps, float* out,
+                     float* deg, cudaStream_t st);
+void batch_trace(const float* M, int batch, int d, float* tr, cudaStream_t st);
+
+void triu_pack(const float* O, int batch, int d, float* v, cudaStream_t st);
+void triu_unpack(const float* dv, int batch, int d, float* dO, cudaStream_t st);
+
+// count sketch in gather form (CSR inverse of the hash): cs_k[b,s] = sum_{j in bucket s} sign*x[b,j]
+void sketch_fwd(const float* x, int batch, int d, int S, const int* off, const int* idx,
+                const float* sgn, float* cs /*[3,B,S]*/, float* out, cudaStream_t st);
+void sketch_bwd(const float* dout, const float* cs, int batch, int d, int S, const long long* hash,
+                const long long* sign /*[3,d] each, int64 as in the state_dict*/, float* dx,
+                cudaStream_t st);
+
+// ---- pooling backward pieces
+// dmu = -(colsum(dZc) + sw*du/(t+eps))
+void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,
+                  int n, int d, float eps, float* dmu, cudaStream_t st);
+// dZ = dZc + w (du + dmu)^T/(t+eps); dw = (Zc du + Z dmu)/(t+eps); dt = -(u.du + mu.dmu)/(t+eps)
+void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w, const float* t,
+                   const float* mu, const float* u, const float* du, const float* dmu, int batch,
+                   int n, int d, float eps, float* dZ, float* dw, float* dt, int prec,
+                   cudaStream_t st);
+// ds_i = sum_j (dWf_ij G_ij s_j + dWf_ji G_ji s_j),  dWf = dW + dw 1^T + dt I
+void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* dt, const float* G,
+                 const float* s, int batch, int n, float* ds, cudaStream_t st);
+// dG_ij = s_i dWf_ij s_j + ddeg_i ;  ddeg = -0.5 * s^3 * ds * [deg >= eps]
+void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
+                 const float* deg, const float* ds, int batch, int n, float eps, float* dG,
+                 cudaStream_t st);
+
+}  // namespace k
+}  // namespace egm

@@ -1,0 +1,426 @@
+"""torch.autograd bindings of the C-ABI operators (forward AND hand-written backward).
+
+Each Function allocates its outputs / saved state / scratch workspace with torch (the library
+never allocates), then calls the extern "C" entry point on the caller's current CUDA stream.
+The reference leaves all of this to autograd over ~2 200 ATen calls per step.
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_state = threading.local()
+_default_precision = os.environ.get("EGM_PRECISION", "fp32")
+
+
+def set_precision(mode: str) -> None:
+    """Select how dense contractions are evaluated: 'fp32' (bf16x3 split on tcgen05, ~1e-5 rel),
+    'bf16' (single tcgen05 pass, ~4e-3 rel) or 'fp32_simt' (FFMA on CUDA cores)."""
+    global _default_precision
+    _lib.precision_id(mode)
+    _default_precision = mode
+
+
+def get_precision() -> str:
+    return getattr(_state, "override", None) or _default_precision
+
+
+class precision:
+    """Context manager: `with precision('bf16'): ...` (thread-local)."""
+
+    def __init__(self, mode: str):
+        _lib.precision_id(mode)
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = getattr(_state, "override", None)
+        _state.override = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        _state.override = self.prev
+        return False
+
+
+def _prec(mode) -> int:
+    return _lib.precision_id(mode if mode is not None else get_precision())
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor, ndim: int) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name}: tensor is on '{t.device}'. This is the B200-native build of the moment-pooling "
+            "path: it runs hand-written sm_100a kernels only and has no CPU fallback.")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if t.dim() != ndim:
+        raise RuntimeError(f"{name}: expected a {ndim}-D tensor, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- GPF
+class _GPFFunction(Function):
+    @staticmethod
+    def forward(ctx, a, p, coef, cosine, eps, symmetric, prec):
+        L = _lib.load()
+        B, N, D = a.shape
+        P, Q = coef.shape[0] - 1, coef.shape[1] - 1
+        dev = a.device
+        ldr = L.egm_gpf_ldr(N)
+        with torch.cuda.device(dev):
+            G = torch.empty(B, N, N, device=dev, dtype=torch.float32)
+            Ra = torch.empty(B, N, ldr, device=dev, dtype=torch.float32)
+            Rp = torch.empty(B, N, ldr, device=dev, dtype=torch.float32)
+            nrm = torch.empty(2, B, N, device=dev, dtype=torch.float32)
+            coef_c = coef.detach().contiguous()
+            ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec), dev)
+            _lib.check(L.egm_gpf_fwd(a.data_ptr(), p.data_ptr(), coef_c.data_ptr(), B, N, D, P, Q,
+                                     int(cosine), float(eps), int(symmetric), G.data_ptr(),
+                                     Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(),
+                                     prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_gpf_fwd")
+        ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm)
+        ctx.cfg = (int(cosine), float(eps), int(symmetric), prec)
+        return G
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dG):
+        L = _lib.load()
+        a, p, coef, Ra, Rp, nrm = ctx.saved_tensors
+        cosine, eps, symmetric, prec = ctx.cfg
+        B, N, D = a.shape
+        P, Q = coef.shape[0] - 1, coef.shape[1] - 1
+        dev = a.device
+        dG = dG.contiguous()
+        with torch.cuda.device(dev):
+            da = torch.empty_like(a)
+            dp = torch.empty_like(p)
+            dcoef = torch.empty_like(coef)
+            ws = _ws(L.egm_gpf_bwd_workspace(B, N, D, P, Q, prec), dev)
+            _lib.check(L.egm_gpf_bwd(dG.data_ptr(), a.data_ptr(), p.data_ptr(), coef.data_ptr(),
+                                     Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(),
+                                     B, N, D, P, Q, cosine, eps, symmetric, da.data_ptr(), dp.data_ptr(),
+                                     dcoef.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_gpf_bwd")
+        return da, dp, dcoef, None, None, None, None
+
+
+def gpf_fused_graph(tokens_anchor, tokens_positive, coef, *, cosine=True, eps=1e-6, symmetric=True,
+                    precision=None):
+    """G = clamp(sym(sum_pq coef[p,q] f_p(R_a) * f_q(R_p)), 0)  (gpf_kernel.py:117-159).
+
+    `coef` is softplus(alpha) [P+1,Q+1]; gradients flow to both token tensors and to coef."""
+    a = _require_cuda_f32("tokens_anchor", tokens_anchor, 3)
+    p = _require_cuda_f32("tokens_positive", tokens_positive, 3)
+    c = _require_cuda_f32("coef", coef, 2)
+    if a.shape != p.shape:
+        raise RuntimeError(f"token shapes differ: {tuple(a.shape)} vs {tuple(p.shape)}")
+    if c.shape[0] > 16 or c.shape[1] > 16:
+        raise RuntimeError("polynomial degrees above 15 are not supported")
+    return _GPFFunction.apply(a, p, c, cosine, eps, symmetric, _prec(precision))
+
+
+# -------------------------------------------------------------------------- pool
+class _PoolFunction(Function):
+    @staticmethod
+    def forward(ctx, Z, G, eps, want_u, prec):
+        L = _lib.load()
+        B, N, D = Z.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            M2 = torch.empty(B, D, D, device=dev, dtype=torch.float32)
+            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
+            state = _ws(L.egm_pool_state_bytes(B, N, D, prec), dev)
+            ws = _ws(L.egm_pool_fwd_workspace(B, N, D, prec), dev)
+            _lib.check(L.egm_pool_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, float(eps), M2.data_ptr(),
+                                      _p(u), vecs.data_ptr(), mu.data_ptr(), state.data_ptr(), prec,
+                                      ws.data_ptr(), ws.numel(), _stream(dev)), "egm_pool_fwd")
+        ctx.save_for_backward(Z, G, vecs, mu, state, *( [u] if want_u else [] ))
+        ctx.cfg = (float(eps), bool(want_u), prec)
+        if want_u:
+            return M2, u
+        return M2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dM2, du=None):
+        L = _lib.load()
+        eps, want_u, prec = ctx.cfg
+        saved = ctx.saved_tensors
+        Z, G, vecs, mu, state = saved[:5]
+        u = saved[5] if want_u else None
+        B, N, D = Z.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            if dM2 is None:
+                dM2 = torch.zeros(B, D, D, device=dev, dtype=torch.float32)
+            dM2 = dM2.contiguous()
+            if du is not None:
+                du = du.contiguous()
+            dZ = torch.empty_like(Z)
+            dG = torch.empty_like(G)
+            ws = _ws(L.egm_pool_bwd_workspace(B, N, D, prec), dev)
+            _lib.check(L.egm_pool_bwd(dM2.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), _p(u),
+                                      vecs.data_ptr(), mu.data_ptr(), state.data_ptr(), B, N, D, eps,
+                                      dZ.data_ptr(), dG.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                      _stream(dev)), "egm_pool_bwd")
+        return dZ, dG, None, None, None
+
+
+def graph_weighted_pool(tokens, graph, *, eps=1e-5, third_order=False, precision=None):
+    """W = D^-1/2 G D^-1/2; mu = Z^T W 1/(tr W+eps); Zc = Z - mu; M2 = Zc^T W Zc
+    (moment_head.py:246-266, 222-244, 288-293) and, if `third_order`, u = Zc^T W 1/(tr W+eps)
+    (moment_head.py:305-311). Returns M2 [B,D,D] or (M2, u [B,D])."""
+    Z = _require_cuda_f32("tokens", tokens, 3)
+    G = _require_cuda_f32("graph", graph, 3)
+    if G.shape != (Z.shape[0], Z.shape[1], Z.shape[1]):
+        raise RuntimeError(f"graph shape {tuple(G.shape)} does not match tokens {tuple(Z.shape)}")
+    return _PoolFunction.apply(Z, G, eps, third_order, _prec(precision))
+
+
+# ---------------------------------------------------------------------------- NS
+class _NSFunction(Function):
+    @staticmethod
+    def forward(ctx, M, iters, eps, post_mode, prec):
+        L = _lib.load()
+        B, D, _ = M.shape
+        dev = M.device
+        with torch.cuda.device(dev):
+            O = torch.empty_like(M)
+            scal = torch.empty(3, B, device=dev, dtype=torch.float32)
+            state = _ws(L.egm_ns_state_bytes(B, D, iters, prec), dev)
+            ws = _ws(L.egm_ns_fwd_workspace(B, D, iters, prec), dev)
+            _lib.check(L.egm_ns_fwd(M.data_ptr(), B, D, int(iters), float(eps), int(post_mode),
+                                    O.data_ptr(), scal.data_ptr(), state.data_ptr(), prec,
+                                    ws.data_ptr(), ws.numel(), _stream(dev)), "egm_ns_fwd")
+        ctx.save_for_backward(M, O, scal, state)
+        ctx.cfg = (int(iters), float(eps), int(post_mode), prec)
+        return O
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dO):
+        L = _lib.load()
+        M, O, scal, state = ctx.saved_tensors
+        iters, eps, post_mode, prec = ctx.cfg
+        B, D, _ = M.shape
+        dev = M.device
+        dO = dO.contiguous()
+        with torch.cuda.device(dev):
+            dM = torch.empty_like(M)
+            ws = _ws(L.egm_ns_bwd_workspace(B, D, iters, prec), dev)
+            _lib.check(L.egm_ns_bwd(dO.data_ptr(), O.data_ptr(), M.data_ptr(), scal.data_ptr(),
+                                    state.data_ptr(), B, D, iters, eps, post_mode, dM.data_ptr(), prec,
+                                    ws.data_ptr(), ws.numel(), _stream(dev)), "egm_ns_bwd")
+        return dM, None, None, None, None
+
+
+def newton_schulz(matrix, num_iterations, eps=1e-5, *, post="divide", precision=None):
+    """Trace-normalised coupled Newton-Schulz, Y0 = I, Z0 = A (moment_head.py:28-70).
+    post='divide': Y_K / sqrt(tr+eps) (NewtonSchulzSqrtm); post='multiply': Y_K * sqrt(tr+eps)
+    (utils/ops.py:122-165)."""
+    M = _require_cuda_f32("matrix", matrix, 3)
+    if M.shape[1] != M.shape[2]:
+        raise RuntimeError(f"expected square matrices, got {tuple(M.shape)}")
+    mode = {"divide": 0, "multiply": 1}[post]
+    return _NSFunction.apply(M, int(num_iterations), eps, mode, _prec(precision))
+
+
+# -------------------------------------------------------------------------- triu
+class _TriuFunction(Function):
+    @staticmethod
+    def forward(ctx, O):
+        L = _lib.load()
+        B, D, _ = O.shape
+        dev = O.device
+        with torch.cuda.device(dev):
+            v = torch.empty(B, D * (D + 1) // 2, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_triu_pack(O.data_ptr(), B, D, v.data_ptr(), _stream(dev)), "egm_triu_pack")
+        ctx.dims = (B, D)
+        return v
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dv):
+        L = _lib.load()
+        B, D = ctx.dims
+        dev = dv.device
+        dv = dv.contiguous()
+        with torch.cuda.device(dev):
+            dO = torch.empty(B, D, D, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_triu_unpack(dv.data_ptr(), B, D, dO.data_ptr(), _stream(dev)),
+                       "egm_triu_unpack")
+        return dO
+
+
+def half_vectorize(matrix):
+    """Row-major upper triangle incl. diagonal, [B,D,D] -> [B,D(D+1)/2] (moment_head.py:202-220)."""
+    O = _require_cuda_f32("matrix", matrix, 3)
+    if O.shape[1] != O.shape[2]:
+        raise RuntimeError(f"expected square matrices, got {tuple(O.shape)}")
+    return _TriuFunction.apply(O)
+
+
+# ------------------------------------------------------------------------ sketch
+def build_sketch_csr(hashes: torch.Tensor, signs: torch.Tensor, sketch_dim: int):
+    """CSR inverse of the three hash maps: bucket s of sketch h sums sgn[h,e]*x[idx[h,e]] for
+    e in [off[h,s], off[h,s+1]). Stable sort keeps the reference's CPU accumulation order."""
+    H, D = hashes.shape
+    if int(hashes.max()) >= sketch_dim or int(hashes.min()) < 0:
+        # same failure the reference hits in scatter_add_ (moment_head.py:110)
+        raise RuntimeError(
+            f"index {int(hashes.max())} is out of bounds for dimension 1 with size {sketch_dim}")
+    order = torch.argsort(hashes, dim=1, stable=True)
+    sorted_h = torch.gather(hashes, 1, order)
+    counts = torch.zeros(H, sketch_dim, dtype=torch.int64, device=hashes.device)
+    counts.scatter_add_(1, sorted_h, torch.ones_like(sorted_h))
+    off = torch.zeros(H, sketch_dim + 1, dtype=torch.int32, device=hashes.device)
+    off[:, 1:] = torch.cumsum(counts, 1).to(torch.int32)
+    sgn = torch.gather(signs, 1, order).to(torch.float32)
+    return off.contiguous(), order.to(torch.int32).contiguous(), sgn.contiguous()
+
+
+class _SketchFunction(Function):
+    @staticmethod
+    def forward(ctx, x, hashes, signs, off, idx, sgn, S):
+        L = _lib.load()
+        B, D = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            cs = torch.empty(3, B, S, device=dev, dtype=torch.float32)
+            out = torch.empty(B, S, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_sketch_fwd(x.data_ptr(), B, D, S, off.data_ptr(), idx.data_ptr(),
+                                        sgn.data_ptr(), cs.data_ptr(), out.data_ptr(), _stream(dev)),
+                       "egm_sketch_fwd")
+        ctx.save_for_backward(cs, hashes, signs)
+        ctx.dims = (B, D, S)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.load()
+        cs, hashes, signs = ctx.saved_tensors
+        B, D, S = ctx.dims
+        dev = dout.device
+        dout = dout.contiguous()
+        with torch.cuda.device(dev):
+            dx = torch.empty(B, D, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_sketch_bwd(dout.data_ptr(), cs.data_ptr(), B, D, S, hashes.data_ptr(),
+                                        signs.data_ptr(), dx.data_ptr(), _stream(dev)), "egm_sketch_bwd")
+        return dx, None, None, None, None, None, None
+
+
+def tensor_sketch(x, hashes, signs, csr, sketch_dim):
+    """prod_k count_sketch_k(x)  (moment_head.py:100-131). hashes/signs: int64 [3,D]."""
+    x = _require_cuda_f32("x", x, 2)
+    off, idx, sgn = csr
+    return _SketchFunction.apply(x, hashes, signs, off, idx, sgn, int(sketch_dim))
+
+
+# ------------------------------------------------------------------ ops helpers
+class _GramFunction(Function):
+    @staticmethod
+    def forward(ctx, x, cosine, eps, prec):
+        L = _lib.load()
+        B, N, D = x.shape
+        dev = x.device
+        with torch.cuda.device(dev):
+            R = torch.empty(B, N, N, device=dev, dtype=torch.float32)
+            nrm = torch.empty(B, N, device=dev, dtype=torch.float32)
+            ws = _ws(L.egm_gram_workspace(B, N, D, prec), dev)
+            _lib.check(L.egm_gram_fwd(x.data_ptr(), B, N, D, int(cosine), float(eps), R.data_ptr(),
+                                      nrm.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_gram_fwd")
+        ctx.save_for_backward(x, nrm)
+        ctx.cfg = (int(cosine), float(eps), prec)
+        return R
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dR):
+        L = _lib.load()
+        x, nrm = ctx.saved_tensors
+        cosine, eps, prec = ctx.cfg
+        B, N, D = x.shape
+        dev = x.device
+        dR = dR.contiguous()
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            ws = _ws(L.egm_gram_workspace(B, N, D, prec), dev)
+            _lib.check(L.egm_gram_bwd(dR.data_ptr(), x.data_ptr(), nrm.data_ptr(), B, N, D, cosine, eps,
+                                      dx.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_gram_bwd")
+        return dx, None, None, None
+
+
+def similarity_matrix(tokens, *, cosine=True, eps=1e-6, precision=None):
+    """R = Xn Xn^T with Xn = x/max(||x||,eps) (cosine) or x (dot)  (gpf_kernel.py:75-94)."""
+    x = _require_cuda_f32("tokens", tokens, 3)
+    return _GramFunction.apply(x, cosine, eps, _prec(precision))
+
+
+def normalize_graph(graph, method: int, eps: float):
+    """Forward-only kernel for utils.ops.normalize_graph; returns (normalised, clamped degrees)."""
+    G = _require_cuda_f32("graph", graph, 3)
+    L = _lib.load()
+    B, N, _ = G.shape
+    dev = G.device
+    with torch.cuda.device(dev):
+        out = torch.empty_like(G)
+        deg = torch.empty(B, N, device=dev, dtype=torch.float32)
+        _lib.check(L.egm_normalize_graph(G.data_ptr(), B, N, int(method), float(eps), out.data_ptr(),
+                                         deg.data_ptr(), _stream(dev)), "egm_normalize_graph")
+    return out, deg
+
+
+def batch_trace(matrices):
+    M = _require_cuda_f32("matrices", matrices, 3)
+    L = _lib.load()
+    B, D, _ = M.shape
+    dev = M.device
+    with torch.cuda.device(dev):
+        tr = torch.empty(B, device=dev, dtype=torch.float32)
+        _lib.check(L.egm_batch_trace(M.data_ptr(), B, D, tr.data_ptr(), _stream(dev)), "egm_batch_trace")
+    return tr
+
+
+def bmm(A, B, *, trans_a=False, trans_b=False, alpha=1.0, precision=None):
+    """alpha * op(A) @ op(B) through the active GEMM engine (diagnostics / benchmark probe)."""
+    A = _require_cuda_f32("A", A, 3)
+    B = _require_cuda_f32("B", B, 3)
+    L = _lib.load()
+    prec = _prec(precision)
+    nb = A.shape[0]
+    M, K = (A.shape[2], A.shape[1]) if trans_a else (A.shape[1], A.shape[2])
+    N = B.shape[1] if trans_b else B.shape[2]
+    dev = A.device
+    with torch.cuda.device(dev):
+        C = torch.empty(nb, M, N, device=dev, dtype=torch.float32)
+        ws = _ws(L.egm_bmm_workspace(nb, M, N, K, prec), dev)
+        _lib.check(L.egm_bmm(A.data_ptr(), int(trans_a), B.data_ptr(), int(trans_b), nb, M, N, K,
+                             float(alpha), C.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                   "egm_bmm")
+    return C

@@ -1,0 +1,128 @@
+/* egm_b200.h - C ABI of the B200-native moment-pooling path of EGO-Moment-CLE-ViT.
+ *
+ * The reference (hibana2077/EGO-Moment-CLE-ViT) has no FFI: the path lives behind the Python
+ * nn.Module API of src/models. This header is the boundary a binding
+ * for that API sits on: every entry point takes plain device pointers, sizes and a CUDA
+ * stream, never allocates, never synchronises, and returns 0 or a negative error code
+ * (EGM_ERR_*); egm_last_error() gives the message. The caller owns every buffer, including
+ * the scratch workspace whose size the matching *_workspace() call returns.
+ *
+ * All tensors are contiguous row-major fp32 unless stated. `prec` selects how the dense
+ * contractions are evaluated (EGM_PREC_*). Buffers marked "state" are opaque (their layout
+ * depends on `prec`); they only need to be passed back unchanged to the matching *_bwd.
+ *
+ * Reference interface each entry point replaces (file:line in the reference tree):
+ *   egm_gpf_fwd/bwd      GraphPolynomialFusion.forward          src/models/gpf_kernel.py:117-159
+ *                        (_compute_similarity :75-94, _hadamard_power :96-115) and its autograd
+ *   egm_pool_fwd/bwd     MomentHead._normalize_weight_matrix    src/models/moment_head.py:246-266
+ *                        MomentHead._graph_weighted_mean        src/models/moment_head.py:222-244
+ *                        centring + M2 = Zc^T W Zc              src/models/moment_head.py:288-293
+ *                        third-order weighted mean u            src/models/moment_head.py:305-311
+ *   egm_ns_fwd/bwd       NewtonSchulzSqrtm.forward              src/models/moment_head.py:28-70
+ *                        matrix_sqrt_newton_schulz (post_mode 1) src/utils/ops.py:122-165
+ *   egm_triu_pack/unpack MomentHead._half_vectorize             src/models/moment_head.py:202-220
+ *                        half_vectorize_symmetric               src/utils/ops.py:100-119
+ *   egm_sketch_fwd/bwd   TensorSketch.forward/_count_sketch     src/models/moment_head.py:100-133
+ *   egm_gram_fwd/bwd     cosine_similarity_matrix               src/utils/ops.py:355-381
+ *   egm_normalize_graph  normalize_graph                        src/utils/ops.py:238-271
+ *   egm_batch_trace      batch_trace                            src/utils/ops.py:316-326
+ */
+#ifndef EGM_B200_H_
+#define EGM_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* egm_stream_t; /* cudaStream_t */
+
+enum {
+  EGM_PREC_FP32_SIMT = 0, /* fp32 FFMA on CUDA cores                                   */
+  EGM_PREC_BF16X3 = 1,    /* fp32 emulated on tcgen05: bf16 hi/lo split, 3 MMAs/product */
+  EGM_PREC_BF16 = 2       /* single bf16 tcgen05 MMA, fp32 accumulate                   */
+};
+enum {
+  EGM_OK = 0,
+  EGM_ERR_ARG = -1,       /* bad argument (null pointer, size, enum)     */
+  EGM_ERR_WORKSPACE = -2, /* workspace / state buffer too small          */
+  EGM_ERR_CUDA = -3       /* a CUDA call or launch failed                */
+};
+
+int egm_version(void);
+const char* egm_last_error(void);
+
+/* ---- Graph Polynomial Fusion ------------------------------------------------------------
+ * a, p [B,N,D]; coef [(P+1)*(Q+1)] = softplus(alpha) on the device; G [B,N,N].
+ * Saved for backward: Ra, Rp [B,N,ldR] with ldR = egm_gpf_ldr(N); nrm_a, nrm_p [B,N]. */
+long long egm_gpf_ldr(int N);
+size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec);
+int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
+                int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
+                float* nrm_p, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+size_t egm_gpf_bwd_workspace(int B, int N, int D, int P, int Q, int prec);
+int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* coef, const float* Ra,
+                const float* Rp, const float* nrm_a, const float* nrm_p, int B, int N, int D, int P,
+                int Q, int cosine, float eps, int symmetric, float* da, float* dp, float* dcoef,
+                int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+
+/* ---- graph-weighted second-order pooling ----------------------------------------------------
+ * Z [B,N,D] tokens, G [B,N,N] graph (any real matrix) -> M2 [B,D,D], optional u [B,D].
+ * Saved: vecs [B, 4N+2] (s, deg, w, wdiag | t, sw), mu [B,D], state (egm_pool_state_bytes). */
+size_t egm_pool_state_bytes(int B, int N, int D, int prec);
+size_t egm_pool_fwd_workspace(int B, int N, int D, int prec);
+int egm_pool_fwd(const float* Z, const float* G, int B, int N, int D, float eps, float* M2, float* u,
+                 float* vecs, float* mu, void* state, int prec, void* ws, size_t ws_bytes,
+                 egm_stream_t stream);
+size_t egm_pool_bwd_workspace(int B, int N, int D, int prec);
+int egm_pool_bwd(const float* dM2, const float* du, const float* Z, const float* G, const float* u,
+                 const float* vecs, const float* mu, const void* state, int B, int N, int D, float eps,
+                 float* dZ, float* dG, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+
+/* ---- iSQRT-COV: trace pre-normalisation, Newton-Schulz, trace post-compensation -------------
+ * M [B,D,D] -> O [B,D,D]. post_mode 0: O = Y_K / sqrt(tr+eps) (NewtonSchulzSqrtm);
+ * post_mode 1: O = Y_K * sqrt(tr+eps) (utils.ops.matrix_sqrt_newton_schulz).
+ * Saved: scal [3,B] (tr, 1/(tr+eps), post scale), state (egm_ns_state_bytes). */
+size_t egm_ns_state_bytes(int B, int D, int iters, int prec);
+size_t egm_ns_fwd_workspace(int B, int D, int iters, int prec);
+int egm_ns_fwd(const float* M, int B, int D, int iters, float eps, int post_mode, float* O,
+               float* scal, void* state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+size_t egm_ns_bwd_workspace(int B, int D, int iters, int prec);
+int egm_ns_bwd(const float* dO, const float* O, const float* M, const float* scal, const void* state,
+               int B, int D, int iters, float eps, int post_mode, float* dM, int prec, void* ws,
+               size_t ws_bytes, egm_stream_t stream);
+
+/* ---- half-vectorisation (row-major upper triangle incl. diagonal) -------------------------- */
+int egm_triu_pack(const float* O, int B, int D, float* v, egm_stream_t stream);
+int egm_triu_unpack(const float* dv, int B, int D, float* dO, egm_stream_t stream);
+
+/* ---- third-order count-sketch product --------------------------------------------------------
+ * x [B,D] -> out [B,S]; cs [3,B,S] saved. off [3,S+1], idx [3,D] (int32) and sgn [3,D] (fp32)
+ * are the CSR inverse of the hash buffers; hash, sign [3,D] int64 are the state_dict buffers. */
+int egm_sketch_fwd(const float* x, int B, int D, int S, const int* off, const int* idx,
+                   const float* sgn, float* cs, float* out, egm_stream_t stream);
+int egm_sketch_bwd(const float* dout, const float* cs, int B, int D, int S, const long long* hash,
+                   const long long* sign, float* dx, egm_stream_t stream);
+
+/* ---- stand-alone matrix helpers (src/utils/ops.py) -------------------------------------------- */
+size_t egm_gram_workspace(int B, int N, int D, int prec);
+int egm_gram_fwd(const float* x, int B, int N, int D, int cosine, float eps, float* R, float* nrm,
+                 int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+int egm_gram_bwd(const float* dR, const float* x, const float* nrm, int B, int N, int D, int cosine,
+                 float eps, float* dx, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+/* method 0: D^-1/2 G D^-1/2 ; method 1: D^-1 G.  deg [B,N] receives the clamped degrees. */
+int egm_normalize_graph(const float* G, int B, int N, int method, float eps, float* out, float* deg,
+                        egm_stream_t stream);
+int egm_batch_trace(const float* M, int B, int D, float* tr, egm_stream_t stream);
+
+/* Plain batched product C = alpha * op(A) op(B) through the active engine (used by the
+ * native tests and the benchmark's tensor-pipe probe). A [B, M|K, K|M], B [B, K|N, N|K]. */
+size_t egm_bmm_workspace(int B, int M, int N, int K, int prec);
+int egm_bmm(const float* A, int transA, const float* Bm, int transB, int B, int M, int N, int K,
+            float alpha, float* C, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGM_B200_H_ */

@@ -1,0 +1,94 @@
+"""Pin oracle/moment_oracle.py against fixtures produced by the reference itself
+(tests/golden/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, params_of, rel_err
+from oracle import moment_oracle as O
+
+SMALL = ["small_p2q2", "small_p3q3_third", "small_dot_nosym", "small_trainbn"]
+
+
+def _cfg(rec):
+    B, N, D, P, Q, K, d_out, third, S, sym, train = [int(v) for v in rec["cfg"]]
+    return dict(B=B, N=N, D=D, P=P, Q=Q, K=K, d_out=d_out, third=bool(third), S=S, sym=bool(sym),
+                train=bool(train), kind=str(rec["similarity"]))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_forward_taps_match_reference(name):
+    rec = golden(name)
+    c = _cfg(rec)
+    fw = O.gpf_forward(rec["anchor"], rec["positive"], rec["alpha"], c["kind"], 1e-6, c["sym"])
+    assert rel_err(fw["G"], rec["G"]) < 1e-12
+    st = O.head_forward(rec["anchor"], fw["G"], params_of(rec), c["K"], c["third"], c["S"], c["train"])
+    for key in ("W", "mu", "M2", "isqrt", "vec", "pre_bn", "out"):
+        assert rel_err(st[key], rec[key]) < 1e-9, key
+    if c["third"]:
+        assert rel_err(st["u"], rec["u"]) < 1e-9
+        assert rel_err(st["sketch"], rec["sketch"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_backward_matches_reference_autograd(name):
+    rec = golden(name)
+    c = _cfg(rec)
+    fw = O.gpf_forward(rec["anchor"], rec["positive"], rec["alpha"], c["kind"], 1e-6, c["sym"])
+    # d vec -> d M2 through iSQRT-COV
+    dO = O.half_vectorize_backward(rec["d_vec"], c["D"])
+    dM = O.newton_schulz_backward(rec["M2"], dO, c["K"], 1e-5)
+    assert rel_err(dM, rec["d_M2"]) < 1e-8
+    # graph / token gradients of the pooling stage, driven by the reference's own d G
+    # (d_G in the fixture is the total gradient of the real forward w.r.t. G)
+    da, dp, dalpha = O.gpf_backward(rec["anchor"], rec["positive"], rec["alpha"], rec["d_G"], c["kind"],
+                                    1e-6, c["sym"])
+    assert rel_err(dalpha, rec["d_alpha"]) < 1e-8
+    assert rel_err(dp, rec["d_positive"]) < 1e-8
+    if not c["train"] and not c["third"]:
+        # eval-mode BN is an affine map: d vec of the real forward equals the tapped d vec
+        dZ, dG = O.moment_backward(rec["anchor"], fw["G"], c["K"], rec["d_vec"], 1e-5)
+        assert rel_err(dG, rec["d_G"]) < 1e-8
+        assert rel_err(dZ + da, rec["d_anchor"]) < 1e-8
+
+
+def test_external_graph_with_third_order():
+    rec = golden("extgraph")
+    B, N, D, K, d_out, S = [int(v) for v in rec["cfg"]]
+    prm = params_of(rec)
+    st = O.head_forward(rec["tokens"], rec["graph"], prm, K, True, S, False)
+    assert rel_err(st["out"], rec["out"]) < 1e-9
+    # full backward incl. the sketch branch: build d vec / d sketch through the (affine, eval-mode)
+    # feature nets analytically
+    d2 = prm["second_net.0.weight"].shape[0]
+    third = {"hashes": [prm[f"tensor_sketch.hash{k}"] for k in (1, 2, 3)],
+             "signs": [prm[f"tensor_sketch.sign{k}"] for k in (1, 2, 3)], "sketch_dim": S}
+
+    def net_bwd(x, prefix, dout):
+        W = prm[f"{prefix}.0.weight"]
+        pre = x @ W.T + prm[f"{prefix}.0.bias"]
+        scale = prm[f"{prefix}.1.weight"] / np.sqrt(prm[f"{prefix}.1.running_var"] + 1e-5)
+        bn = (pre - prm[f"{prefix}.1.running_mean"]) * scale + prm[f"{prefix}.1.bias"]
+        from scipy.special import erf
+        dgelu = 0.5 * (1 + erf(bn / np.sqrt(2))) + bn * np.exp(-bn * bn / 2) / np.sqrt(2 * np.pi)
+        return (dout * dgelu * scale) @ W
+
+    dvec = net_bwd(st["vec"], "second_net", rec["dOut"][:, :d2])
+    dsk = net_bwd(st["sketch"], "third_net", rec["dOut"][:, d2:])
+    dZ, dG = O.moment_backward(rec["tokens"], rec["graph"], K, dvec, 1e-5, third, dsk)
+    assert rel_err(dZ, rec["d_tokens"]) < 1e-8
+    assert rel_err(dG, rec["d_graph"]) < 1e-8
+
+
+def test_ops_helpers():
+    rec = golden("ops")
+    assert rel_err(O.matrix_sqrt_newton_schulz(rec["M"], 5, 1e-5), rec["sqrt_ns"]) < 1e-10
+    assert rel_err(O.half_vectorize(rec["M"]), rec["halfvec"]) == 0.0
+    assert rel_err(O.normalize_graph(rec["graph"], "symmetric"), rec["norm_sym"]) < 1e-12
+    assert rel_err(O.normalize_graph(rec["graph"], "random_walk"), rec["norm_rw"]) < 1e-12
+    assert rel_err(O.batch_trace(rec["M"]), rec["trace"]) < 1e-12
+    assert rel_err(O.cosine_similarity_matrix(rec["feats"]), rec["cos"]) < 1e-12
+    assert rel_err(O.cosine_similarity_matrix(rec["feats"][0][None])[0], rec["cos2d"]) < 1e-12
+    with pytest.raises(ValueError):
+        O.normalize_graph(rec["graph"], "bogus")
+    with pytest.raises(ValueError):
+        O.similarity(rec["feats"], "bogus")
