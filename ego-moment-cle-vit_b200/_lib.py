@@ -31,6 +31,7 @@ _P, _I, _F, _Z, _LL = c_void_p, c_int, c_float, c_size_t, c_longlong
 SIGNATURES = {
     "egm_version": (_I, []),
     "egm_last_error": (c_char_p, []),
+    "egm_launch_count": (ctypes.c_ulonglong, []),
     "egm_gpf_ldr": (_LL, [_I]),
     "egm_gpf_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_gpf_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

@@ -89,6 +89,7 @@ extern "C" {
 
 int egm_version(void) { return 100; }
 const char* egm_last_error(void) { return last_error(); }
+unsigned long long egm_launch_count(void) { return launch_count(); }
 
 // =========================================================================== GPF
 long long egm_gpf_ldr(int N) { return ((long long)N + 3) / 4 * 4; }

@@ -62,6 +62,8 @@ cudaError_t gemm_simt(const GemmProblem& g, cudaStream_t stream);  // all Mats f
 bool gemm_tc_supported(const GemmProblem& g, int npass);
 
 const char* last_error();
+void note_launch();                 // every kernel launch of the library calls this
+unsigned long long launch_count();
 void set_error(const char* fmt, ...);
 
 }  // namespace egm

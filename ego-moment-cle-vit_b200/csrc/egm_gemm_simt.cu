@@ -119,6 +119,7 @@ cudaError_t gemm_simt(const GemmProblem& g, cudaStream_t stream) {
     return cudaErrorInvalidValue;
   }
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
+  note_launch();
   return cudaGetLastError();
 }
 

@@ -442,6 +442,7 @@ cudaError_t launch(const TcParams& p, cudaStream_t stream) {
   const long long ntiles = (long long)p.tiles_m * p.tiles_n * p.batch;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   gemm_tc_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  note_launch();
   return cudaGetLastError();
 }
 

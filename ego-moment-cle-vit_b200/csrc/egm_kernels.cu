@@ -611,29 +611,35 @@ void affine(const float* x, long long ld, long long bs, int batch, int rows, int
   if (vec) {
     dim3 grid((cols / 4 + 127) / 128, rows, batch);
     affine_kernel<4><<<grid, 128, 0, st>>>(x, ld, bs, rows, cols, s, a1, b1, o1, a2, b2, o2, out2 != nullptr);
+  note_launch();
   } else {
     dim3 grid((cols + 127) / 128, rows, batch);
     affine_kernel<1><<<grid, 128, 0, st>>>(x, ld, bs, rows, cols, s, a1, b1, o1, a2, b2, o2, out2 != nullptr);
+  note_launch();
   }
 }
 void export_f32(const W& in, float* out, long long ld, long long bs, int prec, cudaStream_t st) {
   dim3 grid((in.cols + 127) / 128, in.rows, in.batch);
   export_kernel<1><<<grid, 128, 0, st>>>(wptr(in, prec), in.rows, in.cols, out, ld, bs);
+  note_launch();
 }
 void rownorm(const float* x, int batch, int n, int d, float eps, int cosine, float* nrm, const W& xn,
              int prec, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
   rownorm_kernel<<<grid, 256, 0, st>>>(x, n, d, eps, cosine, nrm, wptr(xn, prec));
+  note_launch();
 }
 void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, int n, int d,
                  float eps, float* dx, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
   rownorm_bwd_kernel<<<grid, 256, 0, st>>>(x, nrm, dxn, n, d, eps, dx);
+  note_launch();
 }
 void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
                   int symmetric, int batch, int n, float* G, cudaStream_t st) {
   dim3 grid((n + 127) / 128, n, batch);
   gpf_poly_fwd_kernel<<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+  note_launch();
 }
 int gpf_poly_bwd_blocks(int batch, int n) { return batch * ((n + kPolyBwdRows - 1) / kPolyBwdRows); }
 void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
@@ -643,17 +649,21 @@ void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long l
   dim3 grid((n + kPolyBwdRows - 1) / kPolyBwdRows, batch);
   gpf_poly_bwd_kernel<<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
                                             wptr(Ep, prec), partial);
+  note_launch();
   const int nt = (P + 1) * (Q + 1);
   reduce_partials_kernel<<<nt, 256, 0, st>>>(partial, nblocks, nt, dcoef);
+  note_launch();
 }
 void degree(const float* G, int batch, int n, float eps, float* deg, float* s, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
   degree_kernel<<<grid, 256, 0, st>>>(G, n, eps, deg, s);
+  note_launch();
 }
 void weight(const float* G, const float* s, int batch, int n, const W& Wn, float* w, float* wdiag,
             int prec, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
   weight_kernel<<<grid, 256, 0, st>>>(G, s, n, wptr(Wn, prec), w, wdiag);
+  note_launch();
 }
 void mean_center(const float* Z, const float* w, const float* wdiag, int batch, int n, int d,
                  float eps, float* t, float* sw, float* mu, float* u, const W& Zc, int prec,
@@ -661,54 +671,66 @@ void mean_center(const float* Z, const float* w, const float* wdiag, int batch, 
   dim3 grid((d + 127) / 128, batch);
   mean_center_kernel<<<grid, 128, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu, u,
                                                            wptr(Zc, prec));
+  note_launch();
 }
 void trace_scales(const float* M, int batch, int d, float eps, int post_mode, float* tr, float* inv,
                   float* post, cudaStream_t st) {
   trace_scales_kernel<<<batch, 256, 0, st>>>(M, d, eps, post_mode, tr, inv, post);
+  note_launch();
 }
 void batch_dot(const float* X, const float* Y, int batch, long long n_per, float* out,
                cudaStream_t st) {
   // single deterministic block per image (grid.x = 1): n_per is at most ~1M elements
   dim3 grid(1, batch);
   batch_dot_kernel<<<grid, 1024, 0, st>>>(X, Y, n_per, out);
+  note_launch();
 }
 void ns_bwd_finish(const float* dA, const float* inv, const float* dotO, const float* dotA,
                    float coef_tau, int batch, int d, float* dM, cudaStream_t st) {
   dim3 grid((d + 127) / 128, d, batch);
   ns_bwd_finish_kernel<<<grid, 128, 0, st>>>(dA, inv, dotO, dotA, coef_tau, d, dM);
+  note_launch();
 }
 void normalize_graph(const float* G, int batch, int n, int method, float eps, float* out,
                      float* deg, cudaStream_t st) {
   dim3 g1((n + 7) / 8, batch);
   clamped_degree_kernel<<<g1, 256, 0, st>>>(G, n, eps, deg);
+  note_launch();
   dim3 g2((n + 127) / 128, n, batch);
   normalize_graph_kernel<<<g2, 128, 0, st>>>(G, deg, n, method, out);
+  note_launch();
 }
 void batch_trace(const float* M, int batch, int d, float* tr, cudaStream_t st) {
   batch_trace_kernel<<<batch, 256, 0, st>>>(M, d, tr);
+  note_launch();
 }
 void triu_pack(const float* O, int batch, int d, float* v, cudaStream_t st) {
   dim3 grid((d + 127) / 128, d, batch);
   triu_pack_kernel<<<grid, 128, 0, st>>>(O, d, v);
+  note_launch();
 }
 void triu_unpack(const float* dv, int batch, int d, float* dO, cudaStream_t st) {
   dim3 grid((d + 127) / 128, d, batch);
   triu_unpack_kernel<<<grid, 128, 0, st>>>(dv, d, dO);
+  note_launch();
 }
 void sketch_fwd(const float* x, int batch, int d, int S, const int* off, const int* idx,
                 const float* sgn, float* cs, float* out, cudaStream_t st) {
   dim3 grid((S + 255) / 256, batch);
   sketch_fwd_kernel<<<grid, 256, 0, st>>>(x, batch, d, S, off, idx, sgn, cs, out);
+  note_launch();
 }
 void sketch_bwd(const float* dout, const float* cs, int batch, int d, int S, const long long* hash,
                 const long long* sign, float* dx, cudaStream_t st) {
   dim3 grid((d + 255) / 256, batch);
   sketch_bwd_kernel<<<grid, 256, 0, st>>>(dout, cs, batch, d, S, hash, sign, dx);
+  note_launch();
 }
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,
                   int n, int d, float eps, float* dmu, cudaStream_t st) {
   dim3 grid((d + 127) / 128, batch);
   pool_bwd_dmu_kernel<<<grid, 128, 0, st>>>(dZc, du, sw, t, n, d, eps, dmu);
+  note_launch();
 }
 void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w, const float* t,
                    const float* mu, const float* u, const float* du, const float* dmu, int batch,
@@ -717,17 +739,20 @@ void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w
   dim3 grid((n + 7) / 8, batch);
   pool_bwd_rows_kernel<<<grid, 256, 0, st>>>(dZc, Z, wptr(Zc, prec), w, t, mu, u, du, dmu, n, d, eps,
                                              dZ, dw, dt);
+  note_launch();
 }
 void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* dt, const float* G,
                  const float* s, int batch, int n, float* ds, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
   pool_bwd_ds_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, G, s, n, ds);
+  note_launch();
 }
 void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
                  const float* deg, const float* ds, int batch, int n, float eps, float* dG,
                  cudaStream_t st) {
   dim3 grid((n + 127) / 128, n, batch);
   pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, dG);
+  note_launch();
 }
 
 }  // namespace k

@@ -52,6 +52,8 @@ enum {
 
 int egm_version(void);
 const char* egm_last_error(void);
+/* kernels launched by this library in this process so far (monotonic; bench.py's gpu_launches) */
+unsigned long long egm_launch_count(void);
 
 /* ---- Graph Polynomial Fusion ------------------------------------------------------------
  * a, p [B,N,D]; coef [(P+1)*(Q+1)] = softplus(alpha) on the device; G [B,N,N].

@@ -43,6 +43,26 @@ def _bT(x):
     return np.swapaxes(x, -1, -2)
 
 
+_MM_BACKEND = "numpy"
+
+
+def set_matmul_backend(name):
+    """'numpy' (default) or 'torch': which CPU BLAS evaluates the batched products. bench.py's
+    CPU legs select 'torch' so the port runs on the same threaded torch.bmm the reference itself
+    calls (numpy loops over the batch single-matrix at a time)."""
+    global _MM_BACKEND
+    if name not in ("numpy", "torch"):
+        raise ValueError(name)
+    _MM_BACKEND = name
+
+
+def _mm(a, b):
+    if _MM_BACKEND == "torch" and a.ndim == 3 and b.ndim == 3 and a.dtype == b.dtype:
+        import torch
+        return torch.bmm(torch.from_numpy(a), torch.from_numpy(b)).numpy()   # strided views, no copy
+    return a @ b
+
+
 # ------------------------------------------------------------------------------ GPF
 def l2_normalize(x, eps):
     """F.normalize(tokens, p=2, dim=-1, eps) = x / max(||x||, eps)  (gpf_kernel.py:87)."""
@@ -54,9 +74,9 @@ def similarity(tokens, kind="cosine", eps=1e-6):
     """GraphPolynomialFusion._compute_similarity  (gpf_kernel.py:75-94)."""
     if kind == "cosine":
         xn, _ = l2_normalize(tokens, eps)
-        return xn @ _bT(xn)
+        return _mm(xn, _bT(xn))
     if kind == "dot":
-        return tokens @ _bT(tokens)
+        return _mm(tokens, _bT(tokens))
     raise ValueError(f"Unknown similarity function: {kind}")
 
 
@@ -96,14 +116,15 @@ def gpf_forward(tokens_anchor, tokens_positive, alpha, kind="cosine", eps=1e-6, 
 
 
 def gpf_backward(tokens_anchor, tokens_positive, alpha, dG, kind="cosine", eps=1e-6, symmetric=True,
-                 dtype=np.float64):
-    """Reverse mode of gpf_forward. Returns (d tokens_anchor, d tokens_positive, d alpha)."""
+                 dtype=np.float64, fwd=None):
+    """Reverse mode of gpf_forward. Returns (d tokens_anchor, d tokens_positive, d alpha).
+    `fwd` = the gpf_forward output for the same inputs (reuse instead of recomputing)."""
     a = np.asarray(tokens_anchor, dtype)
     p = np.asarray(tokens_positive, dtype)
     alpha = np.asarray(alpha, dtype)
     dG = np.asarray(dG, dtype)
     P, Q = alpha.shape[0] - 1, alpha.shape[1] - 1
-    fw = gpf_forward(a, p, alpha, kind, eps, symmetric, dtype)
+    fw = fwd if fwd is not None else gpf_forward(a, p, alpha, kind, eps, symmetric, dtype)
     Ra, Rp, c, S = fw["Ra"], fw["Rp"], fw["coef"], fw["S"]
     dS = dG * (S >= 0.0)                       # torch.clamp(min=0) passes the gradient at equality
     dF = 0.5 * (dS + _bT(dS)) if symmetric else dS
@@ -120,9 +141,9 @@ def gpf_backward(tokens_anchor, tokens_positive, alpha, dG, kind="cosine", eps=1
 
     def sim_bwd(x, dR):
         if kind == "dot":
-            return (dR + _bT(dR)) @ x
+            return _mm(dR + _bT(dR), x)
         xn, n = l2_normalize(x, eps)
-        dxn = (dR + _bT(dR)) @ xn
+        dxn = _mm(dR + _bT(dR), xn)
         live = n >= eps                         # clamp_min passes the gradient when ||x|| >= eps
         proj = np.sum(xn * dxn, axis=-1, keepdims=True)
         return np.where(live, (dxn - xn * proj) / np.maximum(n, eps), dxn / eps)
@@ -160,11 +181,11 @@ def newton_schulz(M, iters, eps, post="divide", keep=False):
         if keep:
             Ys.append(Y)
             Zs.append(Z)
-        ZY = Z @ Y
-        YZ = Y @ Z
+        ZY = _mm(Z, Y)
+        YZ = _mm(Y, Z)
         I3 = 3.0 * I
-        Y_new = 0.5 * (Y @ (I3 - ZY))
-        Z = 0.5 * ((I3 - YZ) @ Z)
+        Y_new = 0.5 * _mm(Y, I3 - ZY)
+        Z = 0.5 * _mm(I3 - YZ, Z)
         Y = Y_new
     r = np.sqrt(tr + eps)
     O = Y / r if post == "divide" else Y * r
@@ -173,10 +194,13 @@ def newton_schulz(M, iters, eps, post="divide", keep=False):
     return O
 
 
-def newton_schulz_backward(M, dO, iters, eps, post="divide"):
-    """Reverse mode of newton_schulz."""
+def newton_schulz_backward(M, dO, iters, eps, post="divide", cache=None):
+    """Reverse mode of newton_schulz. `cache` = the second return value of
+    newton_schulz(..., keep=True), to reuse the forward's Y_k / Z_k as autograd would."""
     B, D, _ = M.shape
-    O, (tr, A, YK, Ys, Zs) = newton_schulz(M, iters, eps, post, keep=True)
+    if cache is None:
+        _, cache = newton_schulz(M, iters, eps, post, keep=True)
+    tr, A, YK, Ys, Zs = cache
     I = np.eye(D, dtype=M.dtype)
     te = tr + eps
     if post == "divide":
@@ -188,12 +212,12 @@ def newton_schulz_backward(M, dO, iters, eps, post="divide"):
     dZ = np.zeros_like(M)
     for k in range(iters - 1, -1, -1):
         Y, Z = Ys[k], Zs[k]
-        T1 = 3.0 * I - Z @ Y
-        T2 = 3.0 * I - Y @ Z
-        dT1 = 0.5 * (_bT(Y) @ dY)
-        dT2 = 0.5 * (dZ @ _bT(Z))
-        dY_new = 0.5 * (dY @ _bT(T1)) - _bT(Z) @ dT1 - dT2 @ _bT(Z)
-        dZ_new = 0.5 * (_bT(T2) @ dZ) - dT1 @ _bT(Y) - _bT(Y) @ dT2
+        T1 = 3.0 * I - _mm(Z, Y)
+        T2 = 3.0 * I - _mm(Y, Z)
+        dT1 = 0.5 * _mm(_bT(Y), dY)
+        dT2 = 0.5 * _mm(dZ, _bT(Z))
+        dY_new = 0.5 * _mm(dY, _bT(T1)) - _mm(_bT(Z), dT1) - _mm(dT2, _bT(Z))
+        dZ_new = 0.5 * _mm(_bT(T2), dZ) - _mm(dT1, _bT(Y)) - _mm(_bT(Y), dT2)
         dY, dZ = dY_new, dZ_new
     dA = dZ
     return dA / te + (dtr - np.sum(dA * M, axis=(-1, -2), keepdims=True) / te ** 2) * I
@@ -243,19 +267,25 @@ def tensor_sketch_backward(x, hashes, signs, sketch_dim, dout):
     return dx
 
 
-def moment_forward(tokens, graph, iters, eps=1e-5, third=None, dtype=np.float64):
+def moment_forward(tokens, graph, iters, eps=1e-5, third=None, dtype=np.float64, keep=False):
     """MomentHead.forward up to (and excluding) second_net / third_net (moment_head.py:268-317).
-    `third` = dict(hashes[3,D], signs[3,D], sketch_dim) enables the third-order branch."""
+    `third` = dict(hashes[3,D], signs[3,D], sketch_dim) enables the third-order branch.
+    keep=True also returns what autograd would save (for moment_backward(cache=...))."""
     Z = np.asarray(tokens, dtype)
     G = np.asarray(graph, dtype)
     W, deg, s = normalize_weight_matrix(G, eps)
     mu, w, t = graph_weighted_mean(Z, W, eps)
     Zc = Z - mu[:, None, :]
-    U = W @ Zc
-    M2 = _bT(Zc) @ U
-    isqrt = newton_schulz(M2, iters, eps, "divide")
+    U = _mm(W, Zc)
+    M2 = _mm(_bT(Zc), U)
+    if keep:
+        isqrt, ns_cache = newton_schulz(M2, iters, eps, "divide", keep=True)
+    else:
+        isqrt, ns_cache = newton_schulz(M2, iters, eps, "divide"), None
     vec = half_vectorize(isqrt)
     out = {"W": W, "mu": mu, "Zc": Zc, "M2": M2, "isqrt": isqrt, "vec": vec}
+    if keep:
+        out["cache"] = {"deg": deg, "s": s, "w": w, "t": t, "ns": ns_cache}
     if third is not None:
         tw = W @ np.ones_like(Zc)                                    # moment_head.py:310
         u = (Zc * tw).sum(axis=1) / (t[:, None] + eps)                # moment_head.py:311
@@ -264,20 +294,27 @@ def moment_forward(tokens, graph, iters, eps=1e-5, third=None, dtype=np.float64)
     return out
 
 
-def moment_backward(tokens, graph, iters, dvec, eps=1e-5, third=None, dsketch=None, dtype=np.float64):
-    """Reverse mode of moment_forward: returns (d tokens, d graph) given d vec (and d sketch)."""
+def moment_backward(tokens, graph, iters, dvec, eps=1e-5, third=None, dsketch=None, dtype=np.float64,
+                    fwd=None):
+    """Reverse mode of moment_forward: returns (d tokens, d graph) given d vec (and d sketch).
+    `fwd` = moment_forward(..., keep=True) output, to reuse saved tensors as autograd would."""
     Z = np.asarray(tokens, dtype)
     G = np.asarray(graph, dtype)
     B, N, D = Z.shape
-    W, deg, s = normalize_weight_matrix(G, eps)
-    mu, w, t = graph_weighted_mean(Z, W, eps)
+    if fwd is not None:
+        W, mu, Zc, M2 = fwd["W"], fwd["mu"], fwd["Zc"], fwd["M2"]
+        deg, s, w, t, ns_cache = (fwd["cache"][k] for k in ("deg", "s", "w", "t", "ns"))
+    else:
+        W, deg, s = normalize_weight_matrix(G, eps)
+        mu, w, t = graph_weighted_mean(Z, W, eps)
+        Zc = Z - mu[:, None, :]
+        M2 = _bT(Zc) @ (W @ Zc)
+        ns_cache = None
     te = (t + eps)[:, None]
-    Zc = Z - mu[:, None, :]
-    M2 = _bT(Zc) @ (W @ Zc)
     dO = half_vectorize_backward(np.asarray(dvec, dtype), D)
-    dM = newton_schulz_backward(M2, dO, iters, eps, "divide")
-    dZc = W @ Zc @ _bT(dM) + _bT(W) @ Zc @ dM
-    dW = Zc @ dM @ _bT(Zc)
+    dM = newton_schulz_backward(M2, dO, iters, eps, "divide", cache=ns_cache)
+    dZc = _mm(_mm(W, Zc), _bT(dM)) + _mm(_mm(_bT(W), Zc), dM)
+    dW = _mm(_mm(Zc, dM), _bT(Zc))
     dw = np.zeros((B, N), dtype)
     dt = np.zeros((B,), dtype)
     if third is not None and dsketch is not None:
@@ -372,3 +409,43 @@ def cosine_similarity_matrix(features, eps=1e-8, dtype=np.float64):
 def batch_trace(M):
     """utils/ops.py:316-326."""
     return np.trace(M, axis1=-2, axis2=-1)
+
+
+# ------------------------------------------------- whole-path step (bench.py cpu baseline)
+def feature_net_backward(v, params, prefix, dout, train, bn_eps=1e-5):
+    """d/d v and d/d weight of Linear -> BatchNorm1d -> GELU (dropout inactive)."""
+    Wt = np.asarray(params[f"{prefix}.0.weight"]).astype(v.dtype, copy=False)
+    gamma = np.asarray(params[f"{prefix}.1.weight"], v.dtype)
+    pre = v @ Wt.T + np.asarray(params[f"{prefix}.0.bias"], v.dtype)
+    if train:
+        mean, var = pre.mean(axis=0), pre.var(axis=0)
+    else:
+        mean = np.asarray(params[f"{prefix}.1.running_mean"], v.dtype)
+        var = np.asarray(params[f"{prefix}.1.running_var"], v.dtype)
+    rstd = 1.0 / np.sqrt(var + bn_eps)
+    xhat = (pre - mean) * rstd
+    bn = xhat * gamma + np.asarray(params[f"{prefix}.1.bias"], v.dtype)
+    dbn = dout * (0.5 * (1.0 + _erf(bn / math.sqrt(2.0))) + bn * np.exp(-0.5 * bn * bn) / math.sqrt(2.0 * math.pi))
+    dxhat = dbn * gamma
+    if train:
+        n = pre.shape[0]
+        dpre = rstd / n * (n * dxhat - dxhat.sum(axis=0) - xhat * (dxhat * xhat).sum(axis=0))
+    else:
+        dpre = dxhat * rstd
+    return dpre @ Wt, dpre.T @ v
+
+
+def path_step(anchor, positive, alpha, params, iters, dout, train=True, dtype=np.float32):
+    """One forward+backward of GPF -> MomentHead (2nd order) with the reference's operation
+    count: forward intermediates are kept and reused by the backward exactly as autograd would
+    (20 + 40 Newton-Schulz products). Returns (out, d anchor, d positive, d alpha, d weight)."""
+    a = np.asarray(anchor, dtype)
+    p = np.asarray(positive, dtype)
+    al = np.asarray(alpha, dtype)
+    fw = gpf_forward(a, p, al, dtype=dtype)
+    st = moment_forward(a, fw["G"], iters, 1e-5, None, dtype, keep=True)
+    out, _ = feature_net(st["vec"], params, "second_net", train)
+    dvec, dWt = feature_net_backward(st["vec"], params, "second_net", np.asarray(dout, dtype), train)
+    dZ, dG = moment_backward(a, fw["G"], iters, dvec, 1e-5, dtype=dtype, fwd=st)
+    da, dp, dal = gpf_backward(a, p, al, dG, dtype=dtype, fwd=fw)
+    return out, da + dZ, dp, dal, dWt
