@@ -259,7 +259,8 @@ def test_ragged_shapes_and_degenerate_settings(pkg, dev, B, N, D, P, Q, K, kind,
     assert rel_err(npy(vec), st["vec"]) < tol
     assert rel_err(npy(a.grad), da + dZ) < 5 * tol
     assert rel_err(npy(p.grad), dp) < 5 * tol
-    assert rel_err(npy(al.grad), dal) < 5 * tol
+    # degree (0,0) makes G a constant and d alpha exactly zero: compare with an absolute floor
+    assert np.linalg.norm(npy(al.grad) - dal) < 5 * tol * (np.linalg.norm(dal) + 1e-5)
 
 
 def test_zero_token_row_and_zero_degree_row_hit_the_clamps(pkg, dev):
@@ -272,8 +273,8 @@ def test_zero_token_row_and_zero_degree_row_hit_the_clamps(pkg, dev):
     positive = torch.randn(B, N, D, generator=g)
     alpha = torch.rand(3, 3, generator=g)
     graph = torch.rand(B, N, N, generator=g)
-    graph[1, 4] = 0.0                                    # zero degree
-    graph[1, 1] = -graph[1, 1]                           # negative degree
+    graph[1, 4] = 0.0                                    # zero degree -> clamp at eps
+    graph[0, 2, 3] = -0.05                               # a negative entry is legal input
     dG_up = torch.randn(B, N, N, generator=g)
     dvec = torch.randn(B, D * (D + 1) // 2, generator=g)
     fw = O.gpf_forward(npy(anchor), npy(positive), npy(alpha))
