@@ -27,6 +27,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "egm_gemm.h"
@@ -45,9 +46,13 @@ constexpr int kTileB = BN * BK * 2;   // 32 KiB per plane
 constexpr int kChunk = BK * 128;      // one MN-major TMA box: 64 K-rows x 128 B = 8 KiB
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;        // two 256-column accumulators
+constexpr int kEpiWarpBytes = 8192;   // per epilogue warp: 2 slots x (32 rows x 128 B)
+constexpr int kEpiBytes = 4 * kEpiWarpBytes;
 
 struct alignas(64) TcParams {
   CUtensorMap tm[2][4];  // [term][A_hi, A_lo, B_hi, B_lo]
+  CUtensorMap tmC[3];    // TMA-store maps: C_hi, C_lo (bf16, 64B swizzle), C_f32 (128B swizzle)
+  int tma_cp, tma_cf;    // which outputs leave through TMA stores
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
   int tiles_m, tiles_n;
@@ -69,7 +74,7 @@ struct Cfg {
   static constexpr int kPlanes = (NPASS == 3) ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kTileA + kTileB);      // 96 KiB / 48 KiB
   static constexpr int kStages = (NPASS == 3) ? 2 : 4;                 // 192 KiB of operands
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -81,13 +86,175 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
          (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
 
+// Epilogue of one accumulator tile for one warp: TMEM -> registers -> alpha*acc + beta*I +
+// gamma*E -> bf16 hi/lo planes and/or fp32. `t_addr` addresses this warp's 32 TMEM lanes,
+// `row0` is the warp's first output row, `n0` the first output column of the 256-wide tile.
+// Outputs leave through TMA stores whenever their layout allows it: each lane writes its row
+// of the 32 x 32 chunk into a swizzled (bank-conflict-free) staging slot and one lane issues
+// cp.async.bulk.tensor - full-line writes, no LSU traffic, ragged edges clipped by the
+// tensor map. Two 4 KiB slots per warp alternate (`slot`), so the store of chunk c overlaps
+// the TMEM read of chunk c+1.
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr, int b, int row0,
+                                              int lane, int n0, uint32_t stage_smem, int& slot) {
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(t_addr + c * 32, v);
+    ptx::tmem_ld_wait();
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
+    if (p.beta_eye != 0.f) {
+      const int d = row - col0;
+      if (d >= 0 && d < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j == d) o[j] += p.beta_eye;
+      }
+    }
+    const bool full = (col0 + 32 <= p.N);
+    if (p.e_mode == 1 && row_ok) {
+      const __nv_bfloat16* eh =
+          static_cast<const __nv_bfloat16*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
+      const __nv_bfloat16* el =
+          p.E1 ? static_cast<const __nv_bfloat16*>(p.E1) + b * p.bsE + (long long)row * p.ldE + col0
+               : nullptr;
+      if (full && (p.ldE & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 h = __ldg(reinterpret_cast<const uint4*>(eh) + j);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            o[j * 8 + 2 * w] += p.gamma * __uint_as_float(hw[w] << 16);
+            o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
+          }
+          if (el) {
+            uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
+            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              o[j * 8 + 2 * w] += p.gamma * __uint_as_float(lw[w] << 16);
+              o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) {
+            float e = __bfloat162float(eh[j]);
+            if (el) e += __bfloat162float(el[j]);
+            o[j] += p.gamma * e;
+          }
+      }
+    } else if (p.e_mode == 2 && row_ok) {
+      const float* ef = static_cast<const float*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
+      if (full && (p.ldE & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 e = __ldg(reinterpret_cast<const float4*>(ef) + j);
+          o[4 * j] += p.gamma * e.x;
+          o[4 * j + 1] += p.gamma * e.y;
+          o[4 * j + 2] += p.gamma * e.z;
+          o[4 * j + 3] += p.gamma * e.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) o[j] += p.gamma * ef[j];
+      }
+    }
+    if (p.Cp_hi) {
+      if (p.tma_cp) {
+        const uint32_t buf = stage_smem + slot * 4096;
+        if (lane == 0) ptx::bulk_wait_read<1>();   // the store that used this slot has drained
+        __syncwarp();
+        const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(o[j * 8 + 2 * w], h0, l0);
+            split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
+            hw[w] = pack2(h0, h1);
+            lw[w] = pack2(l0, l1);
+          }
+          const uint32_t off = lane * 64 + ((j ^ sw) << 4);
+          ptx::sts128(buf + off, hw[0], hw[1], hw[2], hw[3]);
+          if (p.Cp_lo) ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&p.tmC[0], buf, col0, row0, b);
+          if (p.Cp_lo) ptx::tma_store_3d(&p.tmC[1], buf + 2048, col0, row0, b);
+          ptx::bulk_commit();
+        }
+        slot ^= 1;
+      } else if (row_ok) {
+        __nv_bfloat16* ch = p.Cp_hi + b * p.bsCp + (long long)row * p.ldCp + col0;
+        __nv_bfloat16* cl = p.Cp_lo ? p.Cp_lo + b * p.bsCp + (long long)row * p.ldCp + col0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) {
+            __nv_bfloat16 h, l;
+            split_bf16(o[j], h, l);
+            ch[j] = h;
+            if (cl) cl[j] = l;
+          }
+      }
+    }
+    if (p.Cf) {
+      if (p.tma_cf) {
+        const uint32_t buf = stage_smem + slot * 4096;
+        if (lane == 0) ptx::bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t sw = lane & 7;              // 128B swizzle: 16B chunk ^= addr bits [7,10)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          ptx::sts128(buf + lane * 128 + ((j ^ sw) << 4), __float_as_uint(o[4 * j]),
+                      __float_as_uint(o[4 * j + 1]), __float_as_uint(o[4 * j + 2]),
+                      __float_as_uint(o[4 * j + 3]));
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&p.tmC[2], buf, col0, row0, b);
+          ptx::bulk_commit();
+        }
+        slot ^= 1;
+      } else if (row_ok) {
+        float* cf = p.Cf + b * p.bsCf + (long long)row * p.ldCf + col0;
+        if (full && (p.ldCf & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(cf)[j] =
+                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) cf[j] = o[j];
+        }
+      }
+    }
+  }
+}
+
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using C = Cfg<NPASS>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B: align the operand ring.
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t bar_base = epi_base + kEpiBytes;
   // barrier block: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -96,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes +
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + kEpiBytes +
                                            8 * (2 * C::kStages + 4));
 
   const int warp = threadIdx.x >> 5;
@@ -226,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int slot = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -235,131 +403,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int n0 = (r % p.tiles_n) * BN;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
-      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_addr + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
-        if (p.beta_eye != 0.f) {
-          const int d = row - col0;
-          if (d >= 0 && d < 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j == d) o[j] += p.beta_eye;
-          }
-        }
-        const bool full = (col0 + 32 <= p.N);
-        if (p.e_mode == 1) {
-          const __nv_bfloat16* eh =
-              static_cast<const __nv_bfloat16*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
-          const __nv_bfloat16* el =
-              p.E1 ? static_cast<const __nv_bfloat16*>(p.E1) + b * p.bsE + (long long)row * p.ldE + col0
-                   : nullptr;
-          if (full && (p.ldE & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 h = __ldg(reinterpret_cast<const uint4*>(eh) + j);
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                o[j * 8 + 2 * w] += p.gamma * __uint_as_float(hw[w] << 16);
-                o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
-              }
-              if (el) {
-                uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
-                const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  o[j * 8 + 2 * w] += p.gamma * __uint_as_float(lw[w] << 16);
-                  o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                float e = __bfloat162float(eh[j]);
-                if (el) e += __bfloat162float(el[j]);
-                o[j] += p.gamma * e;
-              }
-          }
-        } else if (p.e_mode == 2) {
-          const float* ef = static_cast<const float*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
-          if (full && (p.ldE & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 e = __ldg(reinterpret_cast<const float4*>(ef) + j);
-              o[4 * j] += p.gamma * e.x;
-              o[4 * j + 1] += p.gamma * e.y;
-              o[4 * j + 2] += p.gamma * e.z;
-              o[4 * j + 3] += p.gamma * e.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) o[j] += p.gamma * ef[j];
-          }
-        }
-        if (p.Cp_hi) {
-          __nv_bfloat16* ch = p.Cp_hi + b * p.bsCp + (long long)row * p.ldCp + col0;
-          __nv_bfloat16* cl = p.Cp_lo ? p.Cp_lo + b * p.bsCp + (long long)row * p.ldCp + col0 : nullptr;
-          if (full && (p.ldCp & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(o[j * 8 + 2 * w], h0, l0);
-                split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
-                hw[w] = pack2(h0, h1);
-                lw[w] = pack2(l0, l1);
-              }
-              reinterpret_cast<uint4*>(ch)[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (cl) reinterpret_cast<uint4*>(cl)[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                __nv_bfloat16 h, l;
-                split_bf16(o[j], h, l);
-                ch[j] = h;
-                if (cl) cl[j] = l;
-              }
-          }
-        }
-        if (p.Cf) {
-          float* cf = p.Cf + b * p.bsCf + (long long)row * p.ldCf + col0;
-          if (full && (p.ldCf & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(cf)[j] =
-                  make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) cf[j] = o[j];
-          }
-        }
-      }
+      epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b, m0 + q * 32, lane,
+                    n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) ptx::bulk_wait_all();   // staging slots must outlive their TMA stores
   }
 
   ptx::tc_fence_before();
@@ -367,6 +419,203 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------ 2-CTA variant
+// A CTA pair (cluster of 2, one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and HALF of B's 256 columns, so the shared-memory
+// fill per MMA cycle drops by a third versus the 1-CTA kernel and the freed space buys a
+// deeper ring (3 x 64 KiB stages for bf16x3, 6 x 32 KiB for single pass). Only the leader CTA
+// issues MMAs; its commits are multicast to the mbarriers of both CTAs.
+constexpr int kTileBh = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the B tile
+
+template <int NPASS>
+struct Cfg2 {
+  static constexpr int kPlanes = (NPASS == 3) ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kTileA + kTileBh);     // 64 KiB / 32 KiB
+  static constexpr int kStages = (NPASS == 3) ? 3 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
+};
+
+template <int NPASS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  using C = Cfg2<NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t bar_base = epi_base + kEpiBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + C::kStages * C::kStageBytes + kEpiBytes + 8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < p.nterms; ++t)
+      for (int i = 0; i < 4; ++i)
+        if (i % 2 == 0 || NPASS == 3) ptx::prefetch_tensormap(&p.tm[t][i]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::kStages; ++s) {
+        ptx::mbar_init(full_bar(s), 1);    // used in the leader: its own arrive.expect_tx
+        ptx::mbar_init(empty_bar(s), 1);   // multicast commit of the leader's MMA warp
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);   // multicast commit
+        ptx::mbar_init(tempty_bar(a), 8);  // used in the leader: 4 epilogue warps x 2 CTAs
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc_2sm(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int tiles_per_img = p.tiles_m * p.tiles_n;       // tiles_m counts 256-row tiles here
+  const int ntiles = tiles_per_img * p.batch;
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // --------------------------------------------- TMA producer (both CTAs of the pair)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int m0 = (r / p.tiles_n) * (2 * BM) + rank * BM;        // this CTA's 128 rows
+        const int n0 = (r % p.tiles_n) * BN + rank * (BN / 2);        // this CTA's 128 columns of B
+        for (int t = 0; t < p.nterms; ++t) {
+          const int nkb = (p.K[t] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            const uint32_t fb = ptx::mapa(full_bar(stage), 0);         // the leader's barrier
+            const uint32_t sA = smem_base + stage * C::kStageBytes;
+            const uint32_t sB = sA + C::kPlanes * kTileA;
+            const int k0 = kb * BK;
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl) {
+              if (!p.a_mn[t]) {
+                ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, b);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j)
+                  ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk,
+                                       m0 + 64 * j, k0, b);
+              }
+              if (!p.b_mn[t]) {
+                ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, b);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh + j * kChunk,
+                                       n0 + 64 * j, k0, b);
+              }
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int t = 0; t < p.nterms; ++t) {
+          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
+          const uint32_t idesc = ptx::idesc_bf16_f32(2 * BM, BN, a_mn, b_mn);
+          const uint32_t a_step = a_mn ? 2048u : 32u;
+          const uint32_t b_step = b_mn ? 2048u : 32u;
+          const uint32_t a_lbo = a_mn ? kChunk : 0u;
+          const uint32_t b_lbo = b_mn ? kChunk : 0u;
+          const int nkb = (p.K[t] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sA = smem_base + stage * C::kStageBytes;
+            const uint32_t sB = sA + C::kPlanes * kTileA;
+#pragma unroll
+            for (int kk = 0; kk < BK / UK; ++kk) {
+              const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
+              const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
+              if (NPASS == 3) {
+                const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
+                const uint64_t bl = ptx::smem_desc_sw128(sB + kTileBh + kk * b_step, b_lbo, 1024);
+                ptx::mma_bf16_ss_2sm(d_tmem, al, bh, idesc, accumulate);
+                ptx::mma_bf16_ss_2sm(d_tmem, ah, bl, idesc, 1u);
+                ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, 1u);
+              } else {
+                ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, accumulate);
+              }
+              accumulate = 1u;
+            }
+            ptx::tc_commit_2sm(empty_bar(stage), 0x3);   // frees the slot in both CTAs
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        ptx::tc_commit_2sm(tfull_bar(acc), 0x3);         // both CTAs' epilogues may start
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ----------------------------------------------------- epilogue (both CTAs, own rows)
+    const int q = warp & 3;
+    int slot = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int m0 = (r / p.tiles_n) * (2 * BM) + rank * BM;
+      const int n0 = (r % p.tiles_n) * BN;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b, m0 + q * 32, lane,
+                    n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(tempty_bar(acc));
+        else ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();   // neither CTA may retire while its peer can still touch it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 
@@ -414,6 +663,28 @@ bool make_plane_map(CUtensorMap* tm, const void* base, const Mat& m, int batch, 
   return true;
 }
 
+// Output map for the epilogue's TMA stores: {32 cols, 32 rows, 1 image} boxes.
+bool make_store_map(CUtensorMap* tm, void* base, int rows, int cols, long long ld, long long bstride,
+                    int batch, bool f32) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  const int es = f32 ? 4 : 2;
+  const long long bs = (batch > 1) ? bstride : (long long)rows * ld;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)bs * es};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(store) failed (%d): rows=%d cols=%d ld=%lld", (int)r, rows, cols, ld);
+    return false;
+  }
+  return true;
+}
+
 bool plane_ok(const Mat& m, int batch, bool need_lo) {
   if (!m.p0 || (need_lo && !m.p1)) return false;
   if ((reinterpret_cast<uintptr_t>(m.p0) & 15) || (need_lo && (reinterpret_cast<uintptr_t>(m.p1) & 15)))
@@ -446,6 +717,39 @@ cudaError_t launch(const TcParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <int NPASS>
+cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
+  using C = Cfg2<NPASS>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (configured_dev != dev) {
+    e = cudaFuncSetAttribute(gemm_tc2_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured_dev = dev;
+  }
+  int sms = 0;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+  const long long pairs = sms / 2;
+  const int grid = 2 * (int)(ntiles < pairs ? ntiles : pairs);
+  gemm_tc2_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// EGM_GEMM_CTAS=1 selects the single-CTA kernel (kept for A/B measurements); default is the pair.
+int tc_ctas() {
+  static int v = []() {
+    const char* e = getenv("EGM_GEMM_CTAS");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
+
 }  // namespace
 
 bool gemm_tc_supported(const GemmProblem& g, int npass) {
@@ -472,7 +776,8 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   p.N = g.N;
   p.batch = g.batch;
   p.nterms = g.nterms;
-  p.tiles_m = (g.M + BM - 1) / BM;
+  const int ctas = tc_ctas();
+  p.tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   p.tiles_n = (g.N + BN - 1) / BN;
   for (int t = 0; t < g.nterms; ++t) {
     const GemmTerm& gt = g.t[t];
@@ -480,7 +785,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     p.a_mn[t] = gt.transA ? 1 : 0;   // stored [K,M]  -> M-major
     p.b_mn[t] = gt.transB ? 0 : 1;   // stored [K,N]  -> N-major ; [N,K] -> K-major
     const int a_rows = gt.transA ? BK : BM;
-    const int b_rows = gt.transB ? BN : BK;
+    const int b_rows = gt.transB ? BN / ctas : BK;
     // logical extents double as the TMA bounds: whatever lies outside reads as zero
     Mat A = gt.A, B = gt.B;
     A.rows = gt.transA ? gt.K : g.M;
@@ -505,17 +810,33 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     p.bsE = g.E.bstride;
     p.e_mode = g.e_planes ? 1 : 2;
   }
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (g.Cp.p0) {
     p.Cp_hi = static_cast<__nv_bfloat16*>(g.Cp.p0);
     p.Cp_lo = static_cast<__nv_bfloat16*>(g.Cp.p1);
     p.ldCp = g.Cp.ld;
     p.bsCp = g.Cp.bstride;
+    if (g.Cp.ld % 8 == 0 && (g.batch == 1 || g.Cp.bstride % 8 == 0) && al16(g.Cp.p0) &&
+        (!g.Cp.p1 || al16(g.Cp.p1))) {
+      if (!make_store_map(&p.tmC[0], g.Cp.p0, g.M, g.N, g.Cp.ld, g.Cp.bstride, g.batch, false))
+        return cudaErrorInvalidValue;
+      if (g.Cp.p1 && !make_store_map(&p.tmC[1], g.Cp.p1, g.M, g.N, g.Cp.ld, g.Cp.bstride, g.batch, false))
+        return cudaErrorInvalidValue;
+      p.tma_cp = 1;
+    }
   }
   if (g.Cf.p0) {
     p.Cf = static_cast<float*>(g.Cf.p0);
     p.ldCf = g.Cf.ld;
     p.bsCf = g.Cf.bstride;
+    // one staging slot per chunk: fp32 takes the TMA path only when no plane output shares it
+    if (!g.Cp.p0 && g.Cf.ld % 4 == 0 && (g.batch == 1 || g.Cf.bstride % 4 == 0) && al16(g.Cf.p0)) {
+      if (!make_store_map(&p.tmC[2], g.Cf.p0, g.M, g.N, g.Cf.ld, g.Cf.bstride, g.batch, true))
+        return cudaErrorInvalidValue;
+      p.tma_cf = 1;
+    }
   }
+  if (ctas == 2) return npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
   return npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
 }
 
