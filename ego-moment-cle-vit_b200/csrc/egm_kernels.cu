@@ -175,32 +175,51 @@ __global__ void rownorm_bwd_kernel(const float* __restrict__ x, const float* __r
 }
 
 // --------------------------------------------------------------- polynomial
-__device__ __forceinline__ void had_powers(float x, int deg, float* pw) {
+template <int MD>
+__device__ __forceinline__ void had_powers(float x, int deg, float (&pw)[MD + 1]) {
   // f_0 = 1, f_1 = x (NOT clamped), f_k = max(x,0)^k   (gpf_kernel.py:107-115)
   pw[0] = 1.f;
-  if (deg >= 1) pw[1] = x;
+  if (MD >= 1) pw[1] = x;
   const float c = fmaxf(x, 0.f);
   float acc = c;
-  for (int k = 2; k <= deg; ++k) { acc *= c; pw[k] = acc; }
+#pragma unroll
+  for (int k = 2; k <= MD; ++k) {
+    acc *= c;
+    pw[k] = (k <= deg) ? acc : 0.f;
+  }
 }
-__device__ __forceinline__ void had_dpowers(float x, int deg, float* dp) {
+template <int MD>
+__device__ __forceinline__ void had_dpowers(float x, int deg, float (&dp)[MD + 1]) {
   // f'_0 = 0, f'_1 = 1, f'_k = k max(x,0)^(k-1)
   dp[0] = 0.f;
-  if (deg >= 1) dp[1] = 1.f;
+  if (MD >= 1) dp[1] = 1.f;
   const float c = fmaxf(x, 0.f);
   float acc = 1.f;
-  for (int k = 2; k <= deg; ++k) { acc *= c; dp[k] = k * acc; }
+#pragma unroll
+  for (int k = 2; k <= MD; ++k) {
+    acc *= c;
+    dp[k] = (k <= deg) ? k * acc : 0.f;
+  }
 }
-__device__ __forceinline__ float poly_eval(const float* pa, const float* pb, const float* coef, int P, int Q) {
+// sum_{p<=P, q<=Q} coef[p,q] pa[p] pb[q]; coef is stored with row stride (Q+1)
+template <int MD>
+__device__ __forceinline__ float poly_eval(const float (&pa)[MD + 1], const float (&pb)[MD + 1],
+                                           const float* coef, int P, int Q) {
   float f = 0.f;
-  for (int p = 0; p <= P; ++p) {
-    float inner = 0.f;
-    for (int q = 0; q <= Q; ++q) inner = fmaf(coef[p * (Q + 1) + q], pb[q], inner);
-    f = fmaf(pa[p], inner, f);
+#pragma unroll
+  for (int p = 0; p <= MD; ++p) {
+    if (p <= P) {
+      float inner = 0.f;
+#pragma unroll
+      for (int q = 0; q <= MD; ++q)
+        if (q <= Q) inner = fmaf(coef[p * (Q + 1) + q], pb[q], inner);
+      f = fmaf(pa[p], inner, f);
+    }
   }
   return f;
 }
 
+template <int MD>
 __global__ void gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
                                     long long ldR, const float* __restrict__ coef, int P, int Q,
                                     int symmetric, int n, float* __restrict__ G) {
@@ -211,14 +230,14 @@ __global__ void gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* _
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const long long base = (long long)b * n * ldR;
-  float pa[kMaxDeg + 1], pb[kMaxDeg + 1];
-  had_powers(Ra[base + (long long)i * ldR + j], P, pa);
-  had_powers(Rp[base + (long long)i * ldR + j], Q, pb);
-  float f = poly_eval(pa, pb, c, P, Q);
+  float pa[MD + 1], pb[MD + 1];
+  had_powers<MD>(Ra[base + (long long)i * ldR + j], P, pa);
+  had_powers<MD>(Rp[base + (long long)i * ldR + j], Q, pb);
+  float f = poly_eval<MD>(pa, pb, c, P, Q);
   if (symmetric) {
-    had_powers(Ra[base + (long long)j * ldR + i], P, pa);
-    had_powers(Rp[base + (long long)j * ldR + i], Q, pb);
-    const float ft = poly_eval(pa, pb, c, P, Q);
+    had_powers<MD>(Ra[base + (long long)j * ldR + i], P, pa);
+    had_powers<MD>(Rp[base + (long long)j * ldR + i], Q, pb);
+    const float ft = poly_eval<MD>(pa, pb, c, P, Q);
     f = 0.5f * (f + ft);
   }
   G[((long long)b * n + i) * n + j] = fmaxf(f, 0.f);
@@ -226,6 +245,7 @@ __global__ void gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* _
 
 // one block handles a strip of rows of one image; deterministic two-stage dcoef reduction
 constexpr int kPolyBwdRows = 8;
+template <int MD>
 __global__ void __launch_bounds__(256)
 gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
                     const float* __restrict__ Rp, long long ldR, const float* __restrict__ coef,
@@ -248,12 +268,12 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
   for (int e = threadIdx.x; e < kPolyBwdRows * n; e += blockDim.x) {
     const int i = i0 + e / n, j = e % n;
     if (i >= n) break;
-    float pa[kMaxDeg + 1], pb[kMaxDeg + 1], pat[kMaxDeg + 1], pbt[kMaxDeg + 1];
+    float pa[MD + 1], pb[MD + 1], pat[MD + 1], pbt[MD + 1];
     const float ra = Ra[rb + (long long)i * ldR + j], rp = Rp[rb + (long long)i * ldR + j];
     const float rat = Ra[rb + (long long)j * ldR + i], rpt = Rp[rb + (long long)j * ldR + i];
-    had_powers(ra, P, pa); had_powers(rp, Q, pb);
-    had_powers(rat, P, pat); had_powers(rpt, Q, pbt);
-    const float f = poly_eval(pa, pb, c, P, Q), ft = poly_eval(pat, pbt, c, P, Q);
+    had_powers<MD>(ra, P, pa); had_powers<MD>(rp, Q, pb);
+    had_powers<MD>(rat, P, pat); had_powers<MD>(rpt, Q, pbt);
+    const float f = poly_eval<MD>(pa, pb, c, P, Q), ft = poly_eval<MD>(pat, pbt, c, P, Q);
     const float g_ij = dG[gb + (long long)i * n + j], g_ji = dG[gb + (long long)j * n + i];
     float dF_ij, dF_ji;
     if (symmetric) {
@@ -264,27 +284,36 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
       dF_ji = (ft >= 0.f) ? g_ji : 0.f;
     }
     // dRa_ij + dRa_ji  and  dRp_ij + dRp_ji
-    float da[kMaxDeg + 1], db[kMaxDeg + 1], dat[kMaxDeg + 1], dbt[kMaxDeg + 1];
-    had_dpowers(ra, P, da); had_dpowers(rp, Q, db);
-    had_dpowers(rat, P, dat); had_dpowers(rpt, Q, dbt);
-    const float ea = dF_ij * poly_eval(da, pb, c, P, Q) + dF_ji * poly_eval(dat, pbt, c, P, Q);
-    const float ep = dF_ij * poly_eval(pa, db, c, P, Q) + dF_ji * poly_eval(pat, dbt, c, P, Q);
+    float da[MD + 1], db[MD + 1], dat[MD + 1], dbt[MD + 1];
+    had_dpowers<MD>(ra, P, da); had_dpowers<MD>(rp, Q, db);
+    had_dpowers<MD>(rat, P, dat); had_dpowers<MD>(rpt, Q, dbt);
+    const float ea = dF_ij * poly_eval<MD>(da, pb, c, P, Q) + dF_ji * poly_eval<MD>(dat, pbt, c, P, Q);
+    const float ep = dF_ij * poly_eval<MD>(pa, db, c, P, Q) + dF_ji * poly_eval<MD>(pat, dbt, c, P, Q);
     wstore(Ea, (long long)b * Ea.bs + (long long)i * Ea.ld + j, ea);
     wstore(Ep, (long long)b * Ep.bs + (long long)i * Ep.ld + j, ep);
-    if (nt <= 16) {
+    if (MD == 3) {
+      // acc[4p+q]: static register indices; re-packed to the (Q+1)-strided order on output
 #pragma unroll
-      for (int t = 0; t < 16; ++t)
-        if (t < nt) acc[t] = fmaf(dF_ij, pa[t / (Q + 1)] * pb[t % (Q + 1)], acc[t]);
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          acc[pp * 4 + qq] = fmaf(dF_ij, pa[pp < MD + 1 ? pp : 0] * pb[qq < MD + 1 ? qq : 0], acc[pp * 4 + qq]);
     } else {
-      for (int t = 0; t < nt; ++t) atomicAdd(&red[t], dF_ij * pa[t / (Q + 1)] * pb[t % (Q + 1)]);
+      for (int pp = 0; pp <= P; ++pp)
+        for (int qq = 0; qq <= Q; ++qq) atomicAdd(&red[pp * (Q + 1) + qq], dF_ij * pa[pp] * pb[qq]);
     }
   }
   float* out = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * nt;
-  if (nt <= 16) {
-    for (int t = 0; t < nt; ++t) {
-      const float v = block_sum(acc[t], sh);
-      if (threadIdx.x == 0) out[t] = v;
-    }
+  if (MD == 3) {
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        if (pp <= P && qq <= Q) {   // block-uniform
+          const float v = block_sum(acc[pp * 4 + qq], sh);
+          if (threadIdx.x == 0) out[pp * (Q + 1) + qq] = v;
+        }
+      }
   } else {
     __syncthreads();
     for (int t = threadIdx.x; t < nt; t += blockDim.x) out[t] = red[t];
@@ -452,22 +481,32 @@ __global__ void batch_trace_kernel(const float* __restrict__ M, int d, float* __
 }
 
 // ------------------------------------------------------------------- triu
-__global__ void triu_pack_kernel(const float* __restrict__ O, int d, float* __restrict__ v) {
-  const int b = blockIdx.z, i = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d || j < i) return;
+constexpr int kTriuRows = 8;
+__global__ void __launch_bounds__(256) triu_pack_kernel(const float* __restrict__ O, int d,
+                                                        float* __restrict__ v) {
+  const int b = blockIdx.y;
   const long long L = (long long)d * (d + 1) / 2;
-  const long long off = (long long)i * d - (long long)i * (i - 1) / 2 + (j - i);
-  v[(long long)b * L + off] = O[((long long)b * d + i) * d + j];
+  const int i0 = blockIdx.x * kTriuRows;
+  for (int r = 0; r < kTriuRows; ++r) {
+    const int i = i0 + r;
+    if (i >= d) break;
+    const float* src = O + ((long long)b * d + i) * d;
+    float* dst = v + (long long)b * L + (long long)i * d - (long long)i * (i - 1) / 2 - i;
+    for (int j = i + threadIdx.x; j < d; j += blockDim.x) dst[j] = src[j];
+  }
 }
-__global__ void triu_unpack_kernel(const float* __restrict__ dv, int d, float* __restrict__ dO) {
-  const int b = blockIdx.z, i = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d) return;
+__global__ void __launch_bounds__(256) triu_unpack_kernel(const float* __restrict__ dv, int d,
+                                                          float* __restrict__ dO) {
+  const int b = blockIdx.y;
   const long long L = (long long)d * (d + 1) / 2;
-  float x = 0.f;
-  if (j >= i) x = dv[(long long)b * L + (long long)i * d - (long long)i * (i - 1) / 2 + (j - i)];
-  dO[((long long)b * d + i) * d + j] = x;
+  const int i0 = blockIdx.x * kTriuRows;
+  for (int r = 0; r < kTriuRows; ++r) {
+    const int i = i0 + r;
+    if (i >= d) break;
+    float* dst = dO + ((long long)b * d + i) * d;
+    const float* src = dv + (long long)b * L + (long long)i * d - (long long)i * (i - 1) / 2 - i;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) dst[j] = (j >= i) ? src[j] : 0.f;
+  }
 }
 
 // ----------------------------------------------------------------- sketch
@@ -638,7 +677,10 @@ void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, 
 void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
                   int symmetric, int batch, int n, float* G, cudaStream_t st) {
   dim3 grid((n + 127) / 128, n, batch);
-  gpf_poly_fwd_kernel<<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+  if (P <= 3 && Q <= 3)
+    gpf_poly_fwd_kernel<3><<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+  else
+    gpf_poly_fwd_kernel<kMaxDeg><<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
   note_launch();
 }
 int gpf_poly_bwd_blocks(int batch, int n) { return batch * ((n + kPolyBwdRows - 1) / kPolyBwdRows); }
@@ -647,8 +689,12 @@ void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long l
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
                   cudaStream_t st) {
   dim3 grid((n + kPolyBwdRows - 1) / kPolyBwdRows, batch);
-  gpf_poly_bwd_kernel<<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
-                                            wptr(Ep, prec), partial);
+  if (P <= 3 && Q <= 3)
+    gpf_poly_bwd_kernel<3><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
+                                                 wptr(Ep, prec), partial);
+  else
+    gpf_poly_bwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n,
+                                                       wptr(Ea, prec), wptr(Ep, prec), partial);
   note_launch();
   const int nt = (P + 1) * (Q + 1);
   reduce_partials_kernel<<<nt, 256, 0, st>>>(partial, nblocks, nt, dcoef);
@@ -705,13 +751,13 @@ void batch_trace(const float* M, int batch, int d, float* tr, cudaStream_t st) {
   note_launch();
 }
 void triu_pack(const float* O, int batch, int d, float* v, cudaStream_t st) {
-  dim3 grid((d + 127) / 128, d, batch);
-  triu_pack_kernel<<<grid, 128, 0, st>>>(O, d, v);
+  dim3 grid((d + kTriuRows - 1) / kTriuRows, batch);
+  triu_pack_kernel<<<grid, 256, 0, st>>>(O, d, v);
   note_launch();
 }
 void triu_unpack(const float* dv, int batch, int d, float* dO, cudaStream_t st) {
-  dim3 grid((d + 127) / 128, d, batch);
-  triu_unpack_kernel<<<grid, 128, 0, st>>>(dv, d, dO);
+  dim3 grid((d + kTriuRows - 1) / kTriuRows, batch);
+  triu_unpack_kernel<<<grid, 256, 0, st>>>(dv, d, dO);
   note_launch();
 }
 void sketch_fwd(const float* x, int batch, int d, int S, const int* off, const int* idx,
