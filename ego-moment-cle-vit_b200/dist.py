@@ -27,12 +27,16 @@ def shard(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class GradBuckets:
-    """DDP-style gradient reduction: parameters are grouped (in reverse registration order, the
+    """DDP-style gradient reduction. Parameters are grouped (in reverse registration order, the
     order backward produces them) into flat buckets of at most `bucket_bytes`; each bucket is
-    averaged with one all-reduce. `reduce()` launches the all-reduces asynchronously and returns
-    after copying the averaged values back into `.grad`."""
+    averaged with one asynchronous all-reduce. With `overlap=True` (default) a
+    post-accumulate-grad hook launches a bucket's all-reduce the moment its last gradient is
+    written, so the 302 MB `second_net.0.weight` gradient - produced first in backward - travels
+    over NVLink while the Newton-Schulz backward is still running. `reduce()` launches whatever is
+    left, waits, and writes the averages back into `.grad`."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None,
+                 overlap: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.buckets: List[List[torch.nn.Parameter]] = []
@@ -47,32 +51,52 @@ class GradBuckets:
             size += nbytes
         if cur:
             self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, bucket in enumerate(self.buckets) for p in bucket}
+        self._ready = [0] * len(self.buckets)
+        self._inflight = {}
+        self._hooks = []
+        if overlap and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        i = self._bucket_of[id(p)]
+        self._ready[i] += 1
+        if self._ready[i] == len(self.buckets[i]):
+            self._launch(i)
+
+    def _launch(self, i: int) -> None:
+        bucket = self.buckets[i]
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+        inplace = len(grads) == 1 and grads[0].is_contiguous()
+        flat = grads[0].view(-1) if inplace else torch.cat([g.reshape(-1) for g in grads])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight[i] = (work, flat, grads, inplace)
 
     def reduce(self) -> None:
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if not self._active():
             return
         world = dist.get_world_size(self.group)
-        works = []
-        for bucket in self.buckets:
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            if len(grads) == 1 and grads[0].is_contiguous():
-                flat = grads[0].view(-1)           # large single tensors reduce in place
-            else:
-                flat = torch.cat([g.reshape(-1) for g in grads])
-            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True),
-                          flat, bucket, grads))
-        for work, flat, bucket, grads in works:
+        for i in range(len(self.buckets)):
+            if i not in self._inflight:
+                self._launch(i)
+        for i, bucket in enumerate(self.buckets):
+            work, flat, grads, inplace = self._inflight.pop(i)
             work.wait()
             flat.div_(world)
-            if not (len(grads) == 1 and grads[0].is_contiguous()):
+            if not inplace:
                 off = 0
-                for p, g in zip(bucket, grads):
+                for g in grads:
                     n = g.numel()
                     g.copy_(flat[off:off + n].view_as(g))
                     off += n
             for p, g in zip(bucket, grads):
                 if p.grad is None:
                     p.grad = g
+        self._ready = [0] * len(self.buckets)
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

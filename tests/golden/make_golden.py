@@ -41,10 +41,19 @@ def npf(t):
 
 
 def run_case(gk, mh, name, B, N, D, P, Q, K, d_out, third, S, similarity="cosine", symmetric=True,
-             dtype=torch.float64, full=True, train_bn=False):
+             dtype=torch.float64, full=True, train_bn=False, adaptive=None, patch_sketch=False):
     torch.manual_seed(0)
-    gpf = gk.GraphPolynomialFusion(P, Q, similarity=similarity, symmetric_enforce=symmetric)
+    if adaptive:
+        gpf = gk.AdaptiveGraphPolynomialFusion(P, Q, similarity=similarity, symmetric_enforce=symmetric,
+                                               adaptive_type=adaptive)
+    else:
+        gpf = gk.GraphPolynomialFusion(P, Q, similarity=similarity, symmetric_enforce=symmetric)
     head = mh.MomentHead(D, d_out, use_third_order=third, isqrt_iterations=K, sketch_dim=S)
+    if patch_sketch:
+        # the reference caps self.sketch_dim at 4*d_in but still hashes into
+        # [0, sketch_dim) and sizes third_net for the uncapped value; this instance-attribute
+        # overwrite (no source change) is the documented way to make config 3 runnable.
+        head.tensor_sketch.sketch_dim = S
     gpf = gpf.to(dtype)
     head = head.to(dtype)
     for m in head.modules():  # dropout off: parity runs are deterministic
@@ -169,12 +178,28 @@ def run_ops(ops):
     print("ops: ok")
 
 
+def run_new(gk, mh):
+    # BASELINE config 3: third-order sketch dim 8192 at D=768 (needs the documented instance patch)
+    run_case(gk, mh, "cfg3_third_s8192", B=4, N=197, D=768, P=3, Q=3, K=5, d_out=256, third=True,
+             S=8192, dtype=torch.float32, full=False, patch_sketch=True)
+    # BASELINE config 5: Swin-B 384 px final-stage tokens (N=144, D=1024), adaptive GPF class
+    run_case(gk, mh, "cfg5_swin_p3q2", B=4, N=144, D=1024, P=3, Q=2, K=5, d_out=256, third=False,
+             S=0, dtype=torch.float32, full=False, adaptive="global")
+    run_case(gk, mh, "cfg5_swin_p1q1", B=2, N=144, D=1024, P=1, Q=1, K=5, d_out=256, third=False,
+             S=0, dtype=torch.float32, full=False, adaptive="attention")
+
+
+
 def main():
+    only_new = "--new" in sys.argv
     if not os.path.isdir(REF):
         sys.exit(f"reference tree not found at {REF}")
     gk = load_ref("ref_gpf_kernel", "src/models/gpf_kernel.py")
     mh = load_ref("ref_moment_head", "src/models/moment_head.py")
     ops = load_ref("ref_ops", "src/utils/ops.py")
+    if only_new:
+        run_new(gk, mh)
+        return
     run_case(gk, mh, "small_p2q2", B=3, N=12, D=16, P=2, Q=2, K=3, d_out=8, third=False, S=0)
     run_case(gk, mh, "small_p3q3_third", B=3, N=13, D=24, P=3, Q=3, K=5, d_out=10, third=True, S=64)
     run_case(gk, mh, "small_dot_nosym", B=2, N=10, D=16, P=1, Q=2, K=2, d_out=6, third=False, S=0,
@@ -187,6 +212,7 @@ def main():
              S=0, dtype=torch.float32, full=False)
     run_case(gk, mh, "cfg1_trainbn", B=8, N=197, D=768, P=3, Q=3, K=5, d_out=256, third=False,
              S=0, dtype=torch.float32, full=False, train_bn=True)
+    run_new(gk, mh)
 
 
 if __name__ == "__main__":

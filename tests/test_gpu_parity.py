@@ -173,6 +173,54 @@ def test_config1_train_mode_batchnorm(pkg, dev):
     assert rel_err(npy(out), rec["out"]) < 5e-3
 
 
+def _run_config_golden(pkg, dev, name, mode, adaptive=None, patch_sketch=False):
+    rec = golden(name)
+    B, N, D, P, Q, K, d_out, third, S = [int(v) for v in rec["cfg"][:9]]
+    torch.manual_seed(0)
+    if adaptive:
+        gpf = pkg.AdaptiveGraphPolynomialFusion(P, Q, adaptive_type=adaptive)
+    else:
+        gpf = pkg.GraphPolynomialFusion(P, Q)
+    head = pkg.MomentHead(D, d_out, use_third_order=bool(third), isqrt_iterations=K, sketch_dim=S)
+    if patch_sketch:
+        with pytest.raises(RuntimeError, match="out of bounds"):     # the unpatched reference bug
+            head.to(dev).eval()(torch.randn(1, N, D, device=dev), torch.rand(1, N, N, device=dev))
+        head.tensor_sketch.sketch_dim = S        # same instance patch as the oracle
+    head.eval()
+    gpf, head = gpf.to(dev), head.to(dev)
+    w = head.second_net[0].weight.detach().cpu().numpy()
+    assert np.array_equal(w[:2, :8], rec["w_head"])                  # identical initialisation
+    anchor, positive = make_inputs(B, N, D)
+    a = anchor.to(dev).requires_grad_(True)
+    p = positive.to(dev).requires_grad_(True)
+    with pkg.functional.precision(mode):
+        out = head(a, gpf(a, p))
+        (out * torch.from_numpy(rec["dOut"]).to(dev)).sum().backward()
+    to, tg = max(TOL_OUT[mode], 2e-5), max(TOL_GRAD[mode], 2e-4)
+    assert out.shape == (B, d_out)
+    assert rel_err(npy(out), rec["out"]) < to
+    assert rel_err(npy(gpf.alpha_coeffs.grad), rec["d_alpha"]) < tg
+    assert rel_err(npy(a.grad)[:, :4, :16], rec["d_anchor_probe"]) < tg
+    assert rel_err(npy(p.grad)[:, :4, :16], rec["d_positive_probe"]) < tg
+    assert rel_err(np.sqrt((npy(p.grad) ** 2).sum(axis=(1, 2))), rec["d_positive_fro"]) < tg
+    assert rel_err(npy(head.second_net[0].weight.grad)[:4, :32], rec["d_w_probe"]) < tg
+    return gpf, head
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_config3_third_order_sketch_8192(pkg, dev, mode):
+    """BASELINE config 3: 3rd-order Tensor-Sketch (sketch_dim 8192 > 4*768) + 2nd-order iSQRT-COV."""
+    _run_config_golden(pkg, dev, "cfg3_third_s8192", mode, patch_sketch=True)
+
+
+@pytest.mark.parametrize("name,adaptive", [("cfg5_swin_p3q2", "global"), ("cfg5_swin_p1q1", "attention")])
+def test_config5_swin_shape_adaptive_gpf(pkg, dev, name, adaptive):
+    """BASELINE config 5: Swin-B 384px final-stage tokens (N=144, D=1024 -> d=256), adaptive GPF."""
+    gpf, _ = _run_config_golden(pkg, dev, name, "fp32", adaptive=adaptive)
+    if adaptive == "attention":   # registered but unused, exactly like the reference
+        assert all(q.grad is None for q in gpf.coeff_attention.parameters())
+
+
 def test_external_graph_golden_with_third_order(pkg, dev):
     rec = golden("extgraph")
     B, N, D, K, d_out, S = [int(v) for v in rec["cfg"]]
