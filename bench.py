@@ -317,8 +317,17 @@ def run_native(args):
         extras[other] = {"value": B / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o,
                          "tolerance": "rel 2e-2 on outputs" if other == "bf16" else "rel 1e-3"}
         EF.set_precision(args.precision)
-    elif world > 1:
-        pass
+        # opt-in algorithmic variant: Newton-Schulz on N x N matrices
+        EF.set_ns_algorithm("lowrank")
+        for mode in (args.precision, other):
+            EF.set_precision(mode)
+            for i in range(3):
+                resident_step(i)
+            ms_o = timed(resident_step, max(5, args.steps // 2)) / max(5, args.steps // 2)
+            extras[f"lowrank_{mode}"] = {"value": B / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o,
+                                         "note": "same function; iSQRT-COV evaluated in N x N low-rank form"}
+        EF.set_ns_algorithm("dense")
+        EF.set_precision(args.precision)
 
     if rank != 0:
         if world > 1:

@@ -6,7 +6,7 @@ NewtonSchulzSqrtm, TensorSketch and the utils.ops matrix helpers) over a C-ABI C
 bandwidth kernels for the graph / sketch stages. CUDA only - there is no CPU fallback.
 """
 from . import _lib, functional
-from .functional import get_precision, precision, set_precision
+from .functional import get_ns_algorithm, get_precision, precision, set_ns_algorithm, set_precision
 from .models import (AdaptiveGraphPolynomialFusion, GPFKernel, GraphPolynomialFusion, MomentHead,
                      NewtonSchulzSqrtm, TensorSketch)
 from .dropin import install_into
@@ -15,5 +15,5 @@ __version__ = "0.1.0"
 __all__ = [
     'GraphPolynomialFusion', 'AdaptiveGraphPolynomialFusion', 'GPFKernel', 'MomentHead',
     'NewtonSchulzSqrtm', 'TensorSketch', 'functional', 'set_precision', 'get_precision',
-    'precision', 'install_into',
+    'precision', 'set_ns_algorithm', 'get_ns_algorithm', 'install_into',
 ]

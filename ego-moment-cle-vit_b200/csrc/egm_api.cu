@@ -8,63 +8,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/egm_b200.h"
-#include "egm_gemm.h"
-#include "egm_kernels.cuh"
+#include "egm_chain.h"
 
 using namespace egm;
 
+using namespace egm::chain;
+
 namespace {
-
-struct Arena {
-  uint8_t* p;
-  size_t cap, used;
-  Arena(void* base, size_t bytes) : p(static_cast<uint8_t*>(base)), cap(bytes), used(0) {}
-  void* take(size_t bytes) {
-    const size_t a = (used + 255) & ~size_t(255);
-    used = a + bytes;
-    return (used <= cap && p) ? p + a : nullptr;
-  }
-};
-inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
-
-bool prec_ok(int prec) { return prec == PREC_FP32_SIMT || prec == PREC_BF16X3 || prec == PREC_BF16; }
-
-cudaError_t run_gemm(const GemmProblem& g, int prec, cudaStream_t st) {
-  if (prec == PREC_FP32_SIMT) return gemm_simt(g, st);
-  return gemm_tc(g, prec == PREC_BF16X3 ? 3 : 1, st);
-}
-// route a working-matrix output / addend to the right slot of the problem
-void out_w(GemmProblem& g, const W& w, int prec) {
-  if (prec == PREC_FP32_SIMT) g.Cf = w_mat(w, prec); else g.Cp = w_mat(w, prec);
-}
-void addend_w(GemmProblem& g, const W& w, float gamma, int prec) {
-  g.E = w_mat(w, prec);
-  g.e_planes = (prec != PREC_FP32_SIMT);
-  g.gamma = gamma;
-}
-GemmTerm term(const W& A, int tA, const W& B, int tB, int K, int prec) {
-  GemmTerm t;
-  t.A = w_mat(A, prec); t.transA = tA; t.B = w_mat(B, prec); t.transB = tB; t.K = K;
-  return t;
-}
-
-#define EGM_REQUIRE(cond, code, ...)   \
-  do {                                 \
-    if (!(cond)) {                     \
-      set_error(__VA_ARGS__);          \
-      return code;                     \
-    }                                  \
-  } while (0)
-#define EGM_CUDA(expr)                                                              \
-  do {                                                                              \
-    cudaError_t e_ = (expr);                                                        \
-    if (e_ != cudaSuccess) {                                                        \
-      set_error("%s: %s [%s]", #expr, cudaGetErrorString(e_), last_error());        \
-      return EGM_ERR_CUDA;                                                          \
-    }                                                                               \
-  } while (0)
-#define EGM_LAUNCHED() EGM_CUDA(cudaGetLastError())
 
 // -------------------------------------------------------------- NS state layout
 // K iterations store: A, T_0..T_{K-1}, Z_1..Z_{K-1}, Y_2..Y_{K-1}  (Y_1 == T_0)

@@ -4,7 +4,8 @@
 //   * egm_gemm_simt.cu - fp32 FFMA engine for shapes TMA cannot address and for the
 //                        strict-fp32 mode
 //
-//   C[b] = alpha * alpha_b[b] * sum_t op(A_t[b]) * op(B_t[b])  +  beta_eye * I  +  gamma * E[b]
+//   C[b] = alpha * alpha_b[b] * sum_t op(A_t[b]) * op(B_t[b])  +  beta_eye * beta_b[b] * I
+//          +  gamma * gamma_b[b] * E[b]
 //
 // Every dense contraction on the moment-pooling path (Gram matrices, W*Zc, Zc^T*U, the
 // Newton-Schulz chain and all of their backward products) is an instance of this.
@@ -48,7 +49,9 @@ struct GemmProblem {
   float alpha = 1.f;
   const float* alpha_b = nullptr;  // optional per-batch multiplier (device pointer)
   float beta_eye = 0.f;
+  const float* beta_b = nullptr;   // optional per-batch multiplier of beta_eye
   float gamma = 0.f;
+  const float* gamma_b = nullptr;  // optional per-batch multiplier of gamma
   Mat E;             // optional addend, storage given by e_planes
   int e_planes = 0;
   Mat Cp;            // optional output as bf16 planes (p0 == nullptr: absent)

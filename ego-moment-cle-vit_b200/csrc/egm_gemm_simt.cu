@@ -19,6 +19,8 @@ struct SimtParams {
   int nterms, M, N, batch;
   float alpha, beta_eye, gamma;
   const float* alpha_b;
+  const float* beta_b;
+  const float* gamma_b;
   const float* E;
   long long ldE, bsE;
   float* C;
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
     }
   }
   const float a_eff = p.alpha * (p.alpha_b ? p.alpha_b[b] : 1.f);
+  const float beta = p.beta_eye * (p.beta_b ? p.beta_b[b] : 1.f);
+  const float gamma = p.gamma * (p.gamma_b ? p.gamma_b[b] : 1.f);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -81,8 +85,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
       float o = a_eff * acc[i][j];
-      if (m == n) o += p.beta_eye;
-      if (p.E) o += p.gamma * p.E[(long long)b * p.bsE + (long long)m * p.ldE + n];
+      if (m == n) o += beta;
+      if (p.E) o += gamma * p.E[(long long)b * p.bsE + (long long)m * p.ldE + n];
       p.C[(long long)b * p.bsC + (long long)m * p.ldC + n] = o;
     }
   }
@@ -105,6 +109,7 @@ cudaError_t gemm_simt(const GemmProblem& g, cudaStream_t stream) {
   }
   p.nterms = g.nterms; p.M = g.M; p.N = g.N; p.batch = g.batch;
   p.alpha = g.alpha; p.beta_eye = g.beta_eye; p.gamma = g.gamma; p.alpha_b = g.alpha_b;
+  p.beta_b = g.beta_b; p.gamma_b = g.gamma_b;
   if (g.E.p0 && g.gamma != 0.f) {
     if (g.e_planes) {
       set_error("gemm_simt: addend must be fp32");

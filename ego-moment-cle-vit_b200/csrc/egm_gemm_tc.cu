@@ -58,6 +58,8 @@ struct alignas(64) TcParams {
   int tiles_m, tiles_n;
   float alpha, beta_eye, gamma;
   const float* alpha_b;
+  const float* beta_b;
+  const float* gamma_b;
   const void* E0;
   const void* E1;
   long long ldE, bsE;
@@ -99,6 +101,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
+  const float beta = p.beta_eye * (p.beta_b ? __ldg(p.beta_b + b) : 1.f);
+  const float gamma = p.gamma * (p.gamma_b ? __ldg(p.gamma_b + b) : 1.f);
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     const int col0 = n0 + c * 32;
@@ -109,12 +113,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
     float o[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
-    if (p.beta_eye != 0.f) {
+    if (beta != 0.f) {
       const int d = row - col0;
       if (d >= 0 && d < 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j == d) o[j] += p.beta_eye;
+          if (j == d) o[j] += beta;
       }
     }
     const bool full = (col0 + 32 <= p.N);
@@ -131,16 +135,16 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
           const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            o[j * 8 + 2 * w] += p.gamma * __uint_as_float(hw[w] << 16);
-            o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
+            o[j * 8 + 2 * w] += gamma * __uint_as_float(hw[w] << 16);
+            o[j * 8 + 2 * w + 1] += gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
           }
           if (el) {
             uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
             const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              o[j * 8 + 2 * w] += p.gamma * __uint_as_float(lw[w] << 16);
-              o[j * 8 + 2 * w + 1] += p.gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
+              o[j * 8 + 2 * w] += gamma * __uint_as_float(lw[w] << 16);
+              o[j * 8 + 2 * w + 1] += gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
             }
           }
         }
@@ -150,7 +154,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
           if (col0 + j < p.N) {
             float e = __bfloat162float(eh[j]);
             if (el) e += __bfloat162float(el[j]);
-            o[j] += p.gamma * e;
+            o[j] += gamma * e;
           }
       }
     } else if (p.e_mode == 2 && row_ok) {
@@ -159,15 +163,15 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 e = __ldg(reinterpret_cast<const float4*>(ef) + j);
-          o[4 * j] += p.gamma * e.x;
-          o[4 * j + 1] += p.gamma * e.y;
-          o[4 * j + 2] += p.gamma * e.z;
-          o[4 * j + 3] += p.gamma * e.w;
+          o[4 * j] += gamma * e.x;
+          o[4 * j + 1] += gamma * e.y;
+          o[4 * j + 2] += gamma * e.z;
+          o[4 * j + 3] += gamma * e.w;
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) o[j] += p.gamma * ef[j];
+          if (col0 + j < p.N) o[j] += gamma * ef[j];
       }
     }
     if (p.Cp_hi) {
@@ -801,6 +805,8 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   }
   p.alpha = g.alpha;
   p.alpha_b = g.alpha_b;
+  p.beta_b = g.beta_b;
+  p.gamma_b = g.gamma_b;
   p.beta_eye = g.beta_eye;
   p.gamma = g.gamma;
   if (g.E.p0 && g.gamma != 0.f) {

@@ -548,6 +548,62 @@ __global__ void sketch_bwd_kernel(const float* __restrict__ dout, const float* _
   dx[(long long)b * d + j] = a;
 }
 
+// -------------------------------------------------- low-rank chain helpers
+__global__ void w_fill_eye_kernel(WPtr out, int n, float c) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  wstore(out, (long long)b * out.bs + (long long)i * out.ld + j, i == j ? c : 0.f);
+}
+__global__ void w_lincomb_kernel(WPtr out, int rows, int cols, float a, WPtr X, float bb, WPtr Y,
+                                 int hasY, float c, WPtr Z, int hasZ, const float* __restrict__ s_b) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float v = a * wload(X, (long long)b * X.bs + (long long)i * X.ld + j);
+  if (hasY) v += bb * wload(Y, (long long)b * Y.bs + (long long)i * Y.ld + j);
+  if (hasZ) v += c * wload(Z, (long long)b * Z.bs + (long long)i * Z.ld + j);
+  if (s_b) v *= s_b[b];
+  wstore(out, (long long)b * out.bs + (long long)i * out.ld + j, v);
+}
+__global__ void w_dot_kernel(WPtr X, WPtr Y, int rows, int cols, float* __restrict__ out) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  float a = 0.f;
+  for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+    const int i = e / cols, j = e - i * cols;
+    a = fmaf(wload(X, (long long)b * X.bs + (long long)i * X.ld + j),
+             wload(Y, (long long)b * Y.bs + (long long)i * Y.ld + j), a);
+  }
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) out[b] = a;
+}
+__global__ void mlr_scalars_fwd_kernel(const float* __restrict__ tau, int batch, float eps, float aK,
+                                       float* __restrict__ scal) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float taup = tau[b] + eps;
+  const float inv = 1.f / taup, post = rsqrtf(taup);
+  scal[b] = taup;
+  scal[batch + b] = inv;
+  scal[2 * batch + b] = post;
+  scal[3 * batch + b] = post * inv;
+  scal[4 * batch + b] = post * aK;
+}
+__global__ void mlr_scalars_bwd_kernel(const float* __restrict__ scal, int batch, float aK,
+                                       const float* __restrict__ dotOO, const float* __restrict__ trdO,
+                                       const float* __restrict__ dotHs, float* __restrict__ dtaup) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float taup = scal[b], inv = scal[batch + b], post = scal[2 * batch + b];
+  const float c1 = scal[3 * batch + b], betaK = scal[4 * batch + b];
+  const float dc1 = (dotOO[b] - betaK * trdO[b]) / c1;
+  const float dpost = aK * trdO[b] + inv * dc1;
+  // dHs = inv * dH  =>  <dH, H> * taup = <dHs, H> * taup^2
+  const float dinv = post * dc1 + (dotHs ? dotHs[b] * taup * taup : 0.f);
+  dtaup[b] = -inv * inv * dinv - 0.5f * post * inv * dpost;   // taup^-1.5 = post * inv
+}
+
 // ---------------------------------------------------------- pooling backward
 __global__ void __launch_bounds__(128)
 pool_bwd_dmu_kernel(const float* __restrict__ dZc, const float* __restrict__ du,
@@ -770,6 +826,32 @@ void sketch_bwd(const float* dout, const float* cs, int batch, int d, int S, con
                 const long long* sign, float* dx, cudaStream_t st) {
   dim3 grid((d + 255) / 256, batch);
   sketch_bwd_kernel<<<grid, 256, 0, st>>>(dout, cs, batch, d, S, hash, sign, dx);
+  note_launch();
+}
+void w_fill_eye(const W& out, float c, int prec, cudaStream_t st) {
+  dim3 grid((out.cols + 127) / 128, out.rows, out.batch);
+  w_fill_eye_kernel<<<grid, 128, 0, st>>>(wptr(out, prec), out.cols, c);
+  note_launch();
+}
+void w_lincomb(const W& out, float a, const W& X, float b, const W* Y, float c, const W* Z,
+               const float* s_b, int prec, cudaStream_t st) {
+  dim3 grid((out.cols + 127) / 128, out.rows, out.batch);
+  w_lincomb_kernel<<<grid, 128, 0, st>>>(wptr(out, prec), out.rows, out.cols, a, wptr(X, prec), b,
+                                         Y ? wptr(*Y, prec) : WPtr{}, Y != nullptr, c,
+                                         Z ? wptr(*Z, prec) : WPtr{}, Z != nullptr, s_b);
+  note_launch();
+}
+void w_dot(const W& X, const W& Y, float* out, int prec, cudaStream_t st) {
+  w_dot_kernel<<<X.batch, 512, 0, st>>>(wptr(X, prec), wptr(Y, prec), X.rows, X.cols, out);
+  note_launch();
+}
+void mlr_scalars_fwd(const float* tau, int batch, float eps, float aK, float* scal, cudaStream_t st) {
+  mlr_scalars_fwd_kernel<<<(batch + 127) / 128, 128, 0, st>>>(tau, batch, eps, aK, scal);
+  note_launch();
+}
+void mlr_scalars_bwd(const float* scal, int batch, float aK, const float* dotOO, const float* trdO,
+                     const float* dotHs, float* dtaup, cudaStream_t st) {
+  mlr_scalars_bwd_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scal, batch, aK, dotOO, trdO, dotHs, dtaup);
   note_launch();
 }
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

@@ -104,6 +104,18 @@ void sketch_bwd(const float* dout, const float* cs, int batch, int d, int S, con
                 const long long* sign /*[3,d] each, int64 as in the state_dict*/, float* dx,
                 cudaStream_t st);
 
+// ---- working-matrix helpers for the low-rank Newton-Schulz chain (N x N per image)
+void w_fill_eye(const W& out, float c, int prec, cudaStream_t st);                 // out = c I
+// out = s_b[b] * (a X + b Y + c Z)   (Y, Z, s_b optional)
+void w_lincomb(const W& out, float a, const W& X, float b, const W* Y, float c, const W* Z,
+               const float* s_b, int prec, cudaStream_t st);
+void w_dot(const W& X, const W& Y, float* out, int prec, cudaStream_t st);        // out[b] = <X_b, Y_b>
+// scal rows: 0 taup = tau+eps, 1 inv = 1/taup, 2 post = taup^-1/2, 3 c1 = post*inv, 4 betaK = post*aK
+void mlr_scalars_fwd(const float* tau, int batch, float eps, float aK, float* scal, cudaStream_t st);
+// dc1 = (dotOO - betaK trdO)/c1 ; dtaup = -inv^2 (post dc1 + dotHs taup^2) - 0.5 taup^-1.5 (aK trdO + inv dc1)
+void mlr_scalars_bwd(const float* scal, int batch, float aK, const float* dotOO, const float* trdO,
+                     const float* dotHs, float* dtaup, cudaStream_t st);
+
 // ---- pooling backward pieces
 // dmu = -(colsum(dZc) + sw*du/(t+eps))
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

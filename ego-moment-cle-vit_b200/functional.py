@@ -189,6 +189,93 @@ class _PoolFunction(Function):
         return dZ, dG, None, None, None
 
 
+class _MomentLowRankFunction(Function):
+    """Pooling + iSQRT-COV fused, Newton-Schulz evaluated on N x N matrices (csrc/egm_lowrank.cu)."""
+
+    @staticmethod
+    def forward(ctx, Z, G, iters, eps, want_u, prec):
+        L = _lib.load()
+        B, N, D = Z.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            O = torch.empty(B, D, D, device=dev, dtype=torch.float32)
+            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
+            scal = torch.empty(5, B, device=dev, dtype=torch.float32)
+            state = _ws(L.egm_mlr_state_bytes(B, N, D, iters, prec), dev)
+            ws = _ws(L.egm_mlr_fwd_workspace(B, N, D, iters, prec), dev)
+            _lib.check(L.egm_mlr_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps),
+                                     O.data_ptr(), _p(u), vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(),
+                                     state.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_mlr_fwd")
+        ctx.save_for_backward(Z, G, O, vecs, mu, scal, state, *([u] if want_u else []))
+        ctx.cfg = (int(iters), float(eps), bool(want_u), prec)
+        if want_u:
+            return O, u
+        return O
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dO, du=None):
+        L = _lib.load()
+        iters, eps, want_u, prec = ctx.cfg
+        saved = ctx.saved_tensors
+        Z, G, O, vecs, mu, scal, state = saved[:7]
+        u = saved[7] if want_u else None
+        B, N, D = Z.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            if dO is None:
+                dO = torch.zeros(B, D, D, device=dev, dtype=torch.float32)
+            dO = dO.contiguous()
+            if du is not None:
+                du = du.contiguous()
+            dZ = torch.empty_like(Z)
+            dG = torch.empty_like(G)
+            ws = _ws(L.egm_mlr_bwd_workspace(B, N, D, iters, prec), dev)
+            _lib.check(L.egm_mlr_bwd(dO.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), O.data_ptr(), _p(u),
+                                     vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
+                                     B, N, D, iters, eps, dZ.data_ptr(), dG.data_ptr(), prec,
+                                     ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mlr_bwd")
+        return dZ, dG, None, None, None, None
+
+
+_ns_algorithm = os.environ.get("EGM_NS_ALGORITHM", "dense")
+
+
+def set_ns_algorithm(name: str) -> None:
+    """How MomentHead evaluates pooling + iSQRT-COV: 'dense' (D x D Newton-Schulz chain, the
+    reference's formulation) or 'lowrank' (same function, all Newton-Schulz products on N x N
+    matrices when N < D). NewtonSchulzSqrtm on its own is always dense."""
+    global _ns_algorithm
+    if name not in ("dense", "lowrank"):
+        raise ValueError(f"unknown Newton-Schulz algorithm {name!r}; expected 'dense' or 'lowrank'")
+    _ns_algorithm = name
+
+
+def get_ns_algorithm() -> str:
+    return _ns_algorithm
+
+
+def moment_isqrt(tokens, graph, num_iterations, *, eps=1e-5, third_order=False, precision=None,
+                 algorithm=None):
+    """iSQRT-COV of the graph-weighted second moment: NewtonSchulzSqrtm(Zc^T W Zc)
+    (moment_head.py:279-296) [+ u for the third-order branch]. Returns O [B,D,D] or (O, u)."""
+    algo = algorithm or _ns_algorithm
+    Z = _require_cuda_f32("tokens", tokens, 3)
+    G = _require_cuda_f32("graph", graph, 3)
+    if G.shape != (Z.shape[0], Z.shape[1], Z.shape[1]):
+        raise RuntimeError(f"graph shape {tuple(G.shape)} does not match tokens {tuple(Z.shape)}")
+    if algo == "lowrank" and num_iterations >= 1 and Z.shape[1] < Z.shape[2]:
+        return _MomentLowRankFunction.apply(Z, G, int(num_iterations), eps, third_order, _prec(precision))
+    if third_order:
+        M2, u = _PoolFunction.apply(Z, G, eps, True, _prec(precision))
+        return newton_schulz(M2, num_iterations, eps, precision=precision), u
+    M2 = _PoolFunction.apply(Z, G, eps, False, _prec(precision))
+    return newton_schulz(M2, num_iterations, eps, precision=precision)
+
+
 def graph_weighted_pool(tokens, graph, *, eps=1e-5, third_order=False, precision=None):
     """W = D^-1/2 G D^-1/2; mu = Z^T W 1/(tr W+eps); Zc = Z - mu; M2 = Zc^T W Zc
     (moment_head.py:246-266, 222-244, 288-293) and, if `third_order`, u = Zc^T W 1/(tr W+eps)

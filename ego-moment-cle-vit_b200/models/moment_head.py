@@ -125,11 +125,17 @@ class MomentHead(nn.Module):
         return torch.einsum('bn,bnd->bd', w, tokens) / (tr + self.eps)
 
     def forward(self, tokens: torch.Tensor, graph: torch.Tensor) -> torch.Tensor:
-        if self.use_third_order:
-            M2, u = EF.graph_weighted_pool(tokens, graph, eps=self.eps, third_order=True)
+        if EF.get_ns_algorithm() == "lowrank":
+            # opt-in: same function, Newton-Schulz on N x N matrices (functional.moment_isqrt)
+            res = EF.moment_isqrt(tokens, graph, self.isqrt_cov.num_iterations, eps=self.eps,
+                                  third_order=self.use_third_order)
+            M2_normalized, u = res if self.use_third_order else (res, None)
         else:
-            M2 = EF.graph_weighted_pool(tokens, graph, eps=self.eps, third_order=False)
-        M2_normalized = self.isqrt_cov(M2)
+            if self.use_third_order:
+                M2, u = EF.graph_weighted_pool(tokens, graph, eps=self.eps, third_order=True)
+            else:
+                M2 = EF.graph_weighted_pool(tokens, graph, eps=self.eps, third_order=False)
+            M2_normalized = self.isqrt_cov(M2)
         M2_vec = EF.half_vectorize(M2_normalized)
         features = [self.second_net(M2_vec)]
         if self.use_third_order:

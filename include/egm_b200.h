@@ -20,6 +20,7 @@
  *                        third-order weighted mean u            src/models/moment_head.py:305-311
  *   egm_ns_fwd/bwd       NewtonSchulzSqrtm.forward              src/models/moment_head.py:28-70
  *                        matrix_sqrt_newton_schulz (post_mode 1) src/utils/ops.py:122-165
+ *   egm_mlr_fwd/bwd      the same pooling + iSQRT-COV lines, low-rank evaluation (opt-in)
  *   egm_triu_pack/unpack MomentHead._half_vectorize             src/models/moment_head.py:202-220
  *                        half_vectorize_symmetric               src/utils/ops.py:100-119
  *   egm_sketch_fwd/bwd   TensorSketch.forward/_count_sketch     src/models/moment_head.py:100-133
@@ -94,6 +95,21 @@ size_t egm_ns_bwd_workspace(int B, int D, int iters, int prec);
 int egm_ns_bwd(const float* dO, const float* O, const float* M, const float* scal, const void* state,
                int B, int D, int iters, float eps, int post_mode, float* dM, int prec, void* ws,
                size_t ws_bytes, egm_stream_t stream);
+
+/* ---- fused pooling + iSQRT-COV in low-rank form (MomentHead when N < D) ----
+ * Same function of (Z, G) as egm_pool_fwd -> egm_ns_fwd(post_mode 0), evaluated with every
+ * Newton-Schulz product on N x N matrices (M2 = Zc^T W Zc has rank <= N): replaces
+ * moment_head.py:279-296. iters >= 1. Saved: vecs, mu (as egm_pool_fwd), scal [5,B], state. */
+size_t egm_mlr_state_bytes(int B, int N, int D, int iters, int prec);
+size_t egm_mlr_fwd_workspace(int B, int N, int D, int iters, int prec);
+int egm_mlr_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps, float* O,
+                float* u, float* vecs, float* mu, float* scal, void* state, int prec, void* ws,
+                size_t ws_bytes, egm_stream_t stream);
+size_t egm_mlr_bwd_workspace(int B, int N, int D, int iters, int prec);
+int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G, const float* O,
+                const float* u, const float* vecs, const float* mu, const float* scal,
+                const void* state, int B, int N, int D, int iters, float eps, float* dZ, float* dG,
+                int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
 
 /* ---- half-vectorisation (row-major upper triangle incl. diagonal) -------------------------- */
 int egm_triu_pack(const float* O, int B, int D, float* v, egm_stream_t stream);

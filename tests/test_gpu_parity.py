@@ -83,6 +83,76 @@ def test_every_stage_and_gradient_matches_the_oracle(pkg, dev, stage_case, mode)
     assert torch.equal(G, G.transpose(-2, -1)) and float(G.detach().min()) >= 0.0
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_lowrank_newton_schulz_is_the_same_function(pkg, dev, stage_case, mode):
+    """functional.moment_isqrt(algorithm='lowrank'): pooling + iSQRT-COV with every Newton-Schulz
+    product on N x N matrices. Same outputs and gradients as the oracle's dense
+    restatement of moment_head.py:279-296."""
+    c = stage_case
+    EF = pkg.functional
+    with EF.precision(mode):
+        a = c["anchor"].to(dev).requires_grad_(True)
+        G = torch.from_numpy(c["fw"]["G"]).float().to(dev).requires_grad_(True)
+        isq, u = EF.moment_isqrt(a, G, c["K"], eps=1e-5, third_order=True, algorithm="lowrank")
+        vec = EF.half_vectorize(isq)
+        h, s = c["hashes"].to(dev), c["signs"].to(dev)
+        sk = EF.tensor_sketch(u, h, s, EF.build_sketch_csr(h, s, c["S"]), c["S"])
+        ((vec * c["dvec"].to(dev)).sum() + (sk * c["dsk"].to(dev)).sum()).backward()
+    to, tg = TOL_OUT[mode], TOL_GRAD[mode]
+    assert rel_err(npy(isq), c["st"]["isqrt"]) < to
+    assert rel_err(npy(u), c["st"]["u"]) < to
+    assert rel_err(npy(G.grad), c["dG"]) < tg
+    dZ, _ = O.moment_backward(npy(c["anchor"]), c["fw"]["G"], c["K"], npy(c["dvec"]), 1e-5,
+                              {"hashes": c["hashes"].numpy(), "signs": c["signs"].numpy(), "sketch_dim": c["S"]},
+                              npy(c["dsk"]))
+    assert rel_err(npy(a.grad), dZ) < tg
+
+
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_lowrank_on_a_nonsymmetric_graph_and_few_iterations(pkg, dev, K):
+    EF = pkg.functional
+    g = torch.Generator().manual_seed(K)
+    B, N, D = 3, 21, 40
+    Z = torch.randn(B, N, D, generator=g)
+    graph = torch.rand(B, N, N, generator=g) + 0.05        # not symmetric
+    dvec = torch.randn(B, D * (D + 1) // 2, generator=g)
+    st = O.moment_forward(npy(Z), npy(graph), K, 1e-5)
+    dZ, dG = O.moment_backward(npy(Z), npy(graph), K, npy(dvec), 1e-5)
+    for mode, tol in (("fp32_simt", 2e-4), ("fp32", 2e-3)):
+        with EF.precision(mode):
+            z = Z.to(dev).requires_grad_(True)
+            gr = graph.to(dev).requires_grad_(True)
+            vec = EF.half_vectorize(EF.moment_isqrt(z, gr, K, eps=1e-5, algorithm="lowrank"))
+            (vec * dvec.to(dev)).sum().backward()
+        assert rel_err(npy(vec), st["vec"]) < tol
+        assert rel_err(npy(z.grad), dZ) < 5 * tol
+        assert rel_err(npy(gr.grad), dG) < 5 * tol
+
+
+def test_moment_head_lowrank_switch(pkg, dev):
+    """set_ns_algorithm('lowrank') changes how MomentHead evaluates, not what."""
+    EF = pkg.functional
+    torch.manual_seed(3)
+    head = pkg.MomentHead(96, 24, use_third_order=True, isqrt_iterations=5, sketch_dim=128).to(dev).eval()
+    gpf = pkg.GraphPolynomialFusion(2, 2).to(dev)
+    a = torch.randn(4, 30, 96, device=dev)
+    p = a + 0.5 * torch.randn_like(a)
+    outs = {}
+    for algo in ("dense", "lowrank"):
+        EF.set_ns_algorithm(algo)
+        try:
+            x = a.clone().requires_grad_(True)
+            out = head(x, gpf(x, p))
+            out.square().sum().backward()
+            outs[algo] = (out.detach(), x.grad.clone())
+        finally:
+            EF.set_ns_algorithm("dense")
+    assert rel_err(npy(outs["lowrank"][0]), npy(outs["dense"][0])) < 1e-3
+    assert rel_err(npy(outs["lowrank"][1]), npy(outs["dense"][1])) < 2e-3
+    with pytest.raises(ValueError):
+        EF.set_ns_algorithm("magic")
+
+
 # ----------------------------------------------------------- golden fixtures (reference)
 def _build_from_golden(pkg, rec, dev):
     B, N, D, P, Q, K, d_out, third, S, sym, train = [int(v) for v in rec["cfg"]]
