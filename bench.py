@@ -11,7 +11,8 @@ batch. Weak scaling: the per-GPU batch is fixed, `value` is the whole-job images
 
   value      inputs already resident in HBM (two rotating 310 MB input sets > 126 MB L2)
   e2e        same step through the public nn.Module API with HOST (pinned) token buffers:
-             H2D copy of both token tensors + D2H read of the loss inside the timed region
+             H2D copy of both token tensors (double-buffered on a copy stream) + D2H read of the
+             loss of every step, all inside the timed region
   roofline   the dominant kernel (tcgen05 GEMM engine, Newton-Schulz chain), timed live with
              CUDA events inside the timed steps, against MEASURED_PEAKS.json
   cpu_baseline  the numpy oracle port of the reference's algorithm on the host cores (bounded
@@ -276,12 +277,44 @@ def run_native(args):
     def resident_step(i):
         step(*dev_inputs[i % 2])
 
-    def e2e_step(i):
+    # end-to-end: every step's tokens start in pinned HOST memory. The copy of step i+1 is issued
+    # on a side stream before step i is computed (a double-buffered loader), and the loss of step
+    # i is read back through a pinned buffer one step later, so neither transfer stalls the GPU;
+    # all copies and read-backs of the K steps happen inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage.append((torch.empty_like(dev_inputs[0][0]), torch.empty_like(dev_inputs[0][1])))
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    e2e_losses = []
+
+    def e2e_prefetch(i):
+        slot = i % 2
         ha, hp = host_inputs[i % 2]
-        sa, sp = stage[0]
-        sa.copy_(ha, non_blocking=True)
-        sp.copy_(hp, non_blocking=True)
-        return float(step(sa, sp).item())      # D2H read of the loss (4 B), synchronises
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])       # the step that last used this slot is done
+            stage[slot][0].copy_(ha, non_blocking=True)
+            stage[slot][1].copy_(hp, non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    def e2e_step(i, last=False):
+        slot = i % 2
+        if i == 0:
+            e2e_prefetch(0)
+        if not last:
+            e2e_prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(copied[slot])
+        loss = step(*stage[slot])
+        consumed[slot].record()
+        loss_host[slot].copy_(loss.detach(), non_blocking=True)     # D2H read of the step's result
+        loss_ready[slot].record()
+        if i > 0:                                                    # consume the previous step's loss
+            loss_ready[1 - slot].synchronize()
+            e2e_losses.append(float(loss_host[1 - slot]))
+        if last:
+            loss_ready[slot].synchronize()
+            e2e_losses.append(float(loss_host[slot]))
 
     mods = sys.modules["ego-moment-cle-vit_b200.models.moment_head"]
     for i in range(max(args.warmup, 3)):
@@ -298,9 +331,15 @@ def run_native(args):
     ns_f = sum(e[0].elapsed_time(e[1]) for e in ns_events) / max(1, len(ns_events))
     ns_b = sum(e[2].elapsed_time(e[3]) for e in ns_events) / max(1, len(ns_events))
     # ---- end to end: host buffers, copies inside the timed region
+    for ev in consumed:
+        ev.record()
+    torch.cuda.synchronize()
     for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+        e2e_step(i, last=(i == 1))
+    torch.cuda.synchronize()
+    e2e_losses.clear()
+    ms_e2e = timed(lambda i: e2e_step(i, last=(i == args.steps - 1)), args.steps)
+    assert len(e2e_losses) == args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
