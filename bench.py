@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--algorithm", default="dense", choices=["dense", "lowrank"],
+                    help="iSQRT-COV evaluation: D x D Newton-Schulz chain, or the N x N low-rank form")
     ap.add_argument("--no-extras", action="store_true", help="skip bf16-mode / cpu-baseline side runs")
     return ap.parse_args()
 
@@ -206,6 +208,7 @@ def run_native(args):
 
     B = args.batch
     EF.set_precision(args.precision)
+    EF.set_ns_algorithm(args.algorithm)
     torch.manual_seed(0)
     gpf = pkg.GraphPolynomialFusion(DEG, DEG).to(dev)
     head = pkg.MomentHead(D_IN, D_OUT, use_third_order=False, isqrt_iterations=NS_ITERS).to(dev).train()
@@ -347,7 +350,7 @@ def run_native(args):
     e2e_value = B * world / (ms_e2e / args.steps * 1e-3)
 
     extras = {}
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and world == 1 and not args.no_extras and args.algorithm == "dense":
         other = "bf16" if args.precision != "bf16" else "fp32"
         EF.set_precision(other)
         for i in range(3):
@@ -413,6 +416,7 @@ def run_native(args):
             "precision": {"fp32": "fp32 via bf16 hi/lo split, 3 tcgen05 MMAs per product, fp32 accumulate",
                           "bf16": "single bf16 tcgen05 MMA, fp32 accumulate",
                           "fp32_simt": "fp32 FFMA"}[args.precision],
+            "ns_algorithm": args.algorithm,
             "l2": "two rotating 310 MB input sets per GPU (> 126 MB L2); no explicit flush"}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},

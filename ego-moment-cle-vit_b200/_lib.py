@@ -52,6 +52,11 @@ SIGNATURES = {
     "egm_mlr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_mlr_bwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
     "egm_mlr_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
+    "egm_linear_state_bytes": (_Z, [_I, _I, _I, _I]),
+    "egm_linear_fwd_workspace": (_Z, [_I, _I, _I, _I]),
+    "egm_linear_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
+    "egm_linear_bwd_workspace": (_Z, [_I, _I, _I, _I]),
+    "egm_linear_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_triu_pack": (_I, [_P, _I, _I, _P, _P]),
     "egm_triu_unpack": (_I, [_P, _I, _I, _P, _P]),
     "egm_sketch_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -542,6 +542,93 @@ int egm_batch_trace(const float* M, int B, int D, float* tr, egm_stream_t stream
   return EGM_OK;
 }
 
+// ======================================================================== linear
+// y = x W^T + bias on the tcgen05 engine (the Linear(D(D+1)/2 -> d) of second_net has K = 295 296:
+// one 256 x 256 output tile, so K is sliced across all CTA pairs and the partial sums reduced).
+static int linear_splits(int M, int N, int K) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  const int nkb = (K + 63) / 64;
+  int s = (sms / 2) / (tiles > 0 ? tiles : 1);
+  if (s > nkb) s = nkb;
+  if (s > 160) s = 160;
+  return s < 1 ? 1 : s;
+}
+size_t egm_linear_state_bytes(int M, int N, int K, int prec) {
+  (void)prec;
+  return pad256(w_bytes(1, M, K)) + pad256(w_bytes(1, N, K)) + 256;
+}
+size_t egm_linear_fwd_workspace(int M, int N, int K, int prec) {
+  (void)K; (void)prec;
+  return pad256((size_t)160 * M * N * 4) + 512;
+}
+int egm_linear_fwd(const float* x, const float* Wt, const float* bias, int M, int N, int K, float* y,
+                   void* state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
+              "egm_linear_fwd: tensor-core precision modes only (got %d)", prec);
+  EGM_REQUIRE(x && Wt && y && state && M > 0 && N > 0 && K > 0, EGM_ERR_ARG, "egm_linear_fwd: bad argument");
+  Arena sa(state, egm_linear_state_bytes(M, N, K, prec));
+  const W Xw = make_w(sa.take(w_bytes(1, M, K)), 1, M, K);
+  const W Ww = make_w(sa.take(w_bytes(1, N, K)), 1, N, K);
+  const int S = linear_splits(M, N, K);
+  Arena ar(ws, ws_bytes);
+  float* partial = static_cast<float*>(ar.take((size_t)S * M * N * 4));
+  EGM_REQUIRE(partial, EGM_ERR_WORKSPACE, "egm_linear_fwd: workspace too small");
+  k::affine(x, K, (long long)M * K, 1, M, K, nullptr, 1.f, 0.f, Xw, 0.f, 0.f, nullptr, prec, st);
+  k::affine(Wt, K, (long long)N * K, 1, N, K, nullptr, 1.f, 0.f, Ww, 0.f, 0.f, nullptr, prec, st);
+  EGM_LAUNCHED();
+  GemmProblem g;
+  g.M = M; g.N = N; g.batch = 1; g.nterms = 1; g.split_k = S;
+  g.t[0] = term(Xw, 0, Ww, 1, K, prec);
+  g.Cf = f32_mat(partial, M, N, N, (long long)M * N);
+  EGM_CUDA(run_gemm(g, prec, st));
+  k::reduce_splits(partial, S, M, N, bias, y, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+size_t egm_linear_bwd_workspace(int M, int N, int K, int prec) {
+  (void)K; (void)prec;
+  return pad256(w_bytes(1, M, N)) + 512;
+}
+int egm_linear_bwd(const float* dy, const void* state, int M, int N, int K, float* dx, float* dW,
+                   float* dbias, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
+              "egm_linear_bwd: tensor-core precision modes only (got %d)", prec);
+  EGM_REQUIRE(dy && state && M > 0 && N > 0 && K > 0, EGM_ERR_ARG, "egm_linear_bwd: bad argument");
+  Arena sa(const_cast<void*>(state), egm_linear_state_bytes(M, N, K, prec));
+  const W Xw = make_w(sa.take(w_bytes(1, M, K)), 1, M, K);
+  const W Ww = make_w(sa.take(w_bytes(1, N, K)), 1, N, K);
+  Arena ar(ws, ws_bytes);
+  void* wdy = ar.take(w_bytes(1, M, N));
+  EGM_REQUIRE(wdy, EGM_ERR_WORKSPACE, "egm_linear_bwd: workspace too small");
+  const W dYw = make_w(wdy, 1, M, N);
+  k::affine(dy, N, (long long)M * N, 1, M, N, nullptr, 1.f, 0.f, dYw, 0.f, 0.f, nullptr, prec, st);
+  EGM_LAUNCHED();
+  if (dx) {  // dx = dy W
+    GemmProblem g;
+    g.M = M; g.N = K; g.batch = 1; g.nterms = 1;
+    g.t[0] = term(dYw, 0, Ww, 0, N, prec);
+    g.Cf = f32_mat(dx, M, K, K, (long long)M * K);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  if (dW) {  // dW = dy^T x
+    GemmProblem g;
+    g.M = N; g.N = K; g.batch = 1; g.nterms = 1;
+    g.t[0] = term(dYw, 1, Xw, 0, M, prec);
+    g.Cf = f32_mat(dW, N, K, K, (long long)N * K);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  if (dbias) {
+    k::colsum(dy, M, N, dbias, st);
+    EGM_LAUNCHED();
+  }
+  return EGM_OK;
+}
+
 size_t egm_bmm_workspace(int B, int M, int N, int K, int prec) {
   (void)prec;
   return pad256(w_bytes(B, M > K ? M : K, M > K ? M : K)) + pad256(w_bytes(B, N > K ? N : K, N > K ? N : K)) + 1024;

@@ -44,6 +44,8 @@ struct GemmTerm {
 struct GemmProblem {
   int M = 0, N = 0, batch = 1;
   int nterms = 1;
+  int split_k = 1;   // tcgen05 engine only: slice K into split_k partial products, written to
+                     // Cf[s] (s = 0..split_k-1, batch stride Cf.bstride); needs batch == 1
   GemmTerm t[2];
   // epilogue
   float alpha = 1.f;

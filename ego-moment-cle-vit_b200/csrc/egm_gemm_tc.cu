@@ -53,6 +53,7 @@ struct alignas(64) TcParams {
   CUtensorMap tm[2][4];  // [term][A_hi, A_lo, B_hi, B_lo]
   CUtensorMap tmC[3];    // TMA-store maps: C_hi, C_lo (bf16, 64B swizzle), C_f32 (128B swizzle)
   int tma_cp, tma_cf;    // which outputs leave through TMA stores
+  int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
   int tiles_m, tiles_n;
@@ -312,9 +313,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int r = tile - b * tiles_per_img;
         const int m0 = (r / p.tiles_n) * BM;
         const int n0 = (r % p.tiles_n) * BN;
+        const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
-          const int nkb = (p.K[t] + BK - 1) / BK;
-          for (int kb = 0; kb < nkb; ++kb) {
+          const int nkb_all = (p.K[t] + BK - 1) / BK;
+          const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
+          const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t fb = full_bar(stage);
             ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
@@ -324,20 +328,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int pl = 0; pl < C::kPlanes; ++pl) {
               if (!p.a_mn[t]) {
-                ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, b);
+                ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j)
-                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j,
-                                   k0, b);
+                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j, k0, bl);
               }
               if (!p.b_mn[t]) {
-                ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, b);
+                ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, bl);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j)
                   ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk,
-                                   n0 + 64 * j, k0, b);
+                                   n0 + 64 * j, k0, bl);
               }
             }
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int bt = tile / tiles_per_img;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -364,8 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const uint32_t b_step = b_mn ? 2048u : 32u;
           const uint32_t a_lbo = a_mn ? kChunk : 0u;
           const uint32_t b_lbo = b_mn ? kChunk : 0u;
-          const int nkb = (p.K[t] + BK - 1) / BK;
-          for (int kb = 0; kb < nkb; ++kb) {
+          const int nkb_all = (p.K[t] + BK - 1) / BK;
+          const int kb_lo = p.splits > 1 ? (int)((long long)bt * nkb_all / p.splits) : 0;
+          const int kb_hi = p.splits > 1 ? (int)((long long)(bt + 1) * nkb_all / p.splits) : nkb_all;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
@@ -506,9 +512,12 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         const int r = tile - b * tiles_per_img;
         const int m0 = (r / p.tiles_n) * (2 * BM) + rank * BM;        // this CTA's 128 rows
         const int n0 = (r % p.tiles_n) * BN + rank * (BN / 2);        // this CTA's 128 columns of B
+        const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
-          const int nkb = (p.K[t] + BK - 1) / BK;
-          for (int kb = 0; kb < nkb; ++kb) {
+          const int nkb_all = (p.K[t] + BK - 1) / BK;
+          const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
+          const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
             if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
             const uint32_t fb = ptx::mapa(full_bar(stage), 0);         // the leader's barrier
@@ -518,20 +527,20 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int pl = 0; pl < C::kPlanes; ++pl) {
               if (!p.a_mn[t]) {
-                ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, b);
+                ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j)
                   ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk,
-                                       m0 + 64 * j, k0, b);
+                                       m0 + 64 * j, k0, bl);
               }
               if (!p.b_mn[t]) {
-                ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, b);
+                ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, bl);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 128; ++j)
                   ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh + j * kChunk,
-                                       n0 + 64 * j, k0, b);
+                                       n0 + 64 * j, k0, bl);
               }
             }
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -547,6 +556,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+        const int bt = tile / tiles_per_img;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -558,8 +568,10 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
           const uint32_t b_step = b_mn ? 2048u : 32u;
           const uint32_t a_lbo = a_mn ? kChunk : 0u;
           const uint32_t b_lbo = b_mn ? kChunk : 0u;
-          const int nkb = (p.K[t] + BK - 1) / BK;
-          for (int kb = 0; kb < nkb; ++kb) {
+          const int nkb_all = (p.K[t] + BK - 1) / BK;
+          const int kb_lo = p.splits > 1 ? (int)((long long)bt * nkb_all / p.splits) : 0;
+          const int kb_hi = p.splits > 1 ? (int)((long long)(bt + 1) * nkb_all / p.splits) : nkb_all;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
@@ -780,6 +792,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   p.N = g.N;
   p.batch = g.batch;
   p.nterms = g.nterms;
+  p.splits = 1;
   const int ctas = tc_ctas();
   p.tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   p.tiles_n = (g.N + BN - 1) / BN;
@@ -796,12 +809,23 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     A.cols = gt.transA ? g.M : gt.K;
     B.rows = gt.transB ? g.N : gt.K;
     B.cols = gt.transB ? gt.K : g.N;
-    if (!make_plane_map(&p.tm[t][0], A.p0, A, g.batch, a_rows)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&p.tm[t][2], B.p0, B, g.batch, b_rows)) return cudaErrorInvalidValue;
+    const int ab_batch = g.split_k > 1 ? 1 : g.batch;
+    if (!make_plane_map(&p.tm[t][0], A.p0, A, ab_batch, a_rows)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&p.tm[t][2], B.p0, B, ab_batch, b_rows)) return cudaErrorInvalidValue;
     if (npass == 3) {
-      if (!make_plane_map(&p.tm[t][1], A.p1, A, g.batch, a_rows)) return cudaErrorInvalidValue;
-      if (!make_plane_map(&p.tm[t][3], B.p1, B, g.batch, b_rows)) return cudaErrorInvalidValue;
+      if (!make_plane_map(&p.tm[t][1], A.p1, A, ab_batch, a_rows)) return cudaErrorInvalidValue;
+      if (!make_plane_map(&p.tm[t][3], B.p1, B, ab_batch, b_rows)) return cudaErrorInvalidValue;
     }
+  }
+  if (g.split_k > 1) {
+    // K-slices of one product; slice s writes partial sums to output batch index s
+    const int nkb = (g.t[0].K + BK - 1) / BK;
+    if (g.nterms != 1 || g.batch != 1 || g.split_k > nkb || g.Cp.p0 || !g.Cf.p0) {
+      set_error("gemm_tc: split-K needs one term, batch 1, an fp32 output and split_k <= K/64");
+      return cudaErrorInvalidValue;
+    }
+    p.splits = g.split_k;
+    p.batch = g.split_k;
   }
   p.alpha = g.alpha;
   p.alpha_b = g.alpha_b;
@@ -836,8 +860,8 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     p.ldCf = g.Cf.ld;
     p.bsCf = g.Cf.bstride;
     // one staging slot per chunk: fp32 takes the TMA path only when no plane output shares it
-    if (!g.Cp.p0 && g.Cf.ld % 4 == 0 && (g.batch == 1 || g.Cf.bstride % 4 == 0) && al16(g.Cf.p0)) {
-      if (!make_store_map(&p.tmC[2], g.Cf.p0, g.M, g.N, g.Cf.ld, g.Cf.bstride, g.batch, true))
+    if (!g.Cp.p0 && g.Cf.ld % 4 == 0 && (p.batch == 1 || g.Cf.bstride % 4 == 0) && al16(g.Cf.p0)) {
+      if (!make_store_map(&p.tmC[2], g.Cf.p0, g.M, g.N, g.Cf.ld, g.Cf.bstride, p.batch, true))
         return cudaErrorInvalidValue;
       p.tma_cf = 1;
     }

@@ -604,6 +604,22 @@ __global__ void mlr_scalars_bwd_kernel(const float* __restrict__ scal, int batch
   dtaup[b] = -inv * inv * dinv - 0.5f * post * inv * dpost;   // taup^-1.5 = post * inv
 }
 
+__global__ void reduce_splits_kernel(const float* __restrict__ partial, int splits, long long mn, int n,
+                                     const float* __restrict__ bias, float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mn) return;
+  float a = bias ? bias[i % n] : 0.f;
+  for (int s = 0; s < splits; ++s) a += partial[(long long)s * mn + i];
+  y[i] = a;
+}
+__global__ void colsum_kernel(const float* __restrict__ x, int m, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float a = 0.f;
+  for (int i = 0; i < m; ++i) a += x[(long long)i * n + j];
+  out[j] = a;
+}
+
 // ---------------------------------------------------------- pooling backward
 __global__ void __launch_bounds__(128)
 pool_bwd_dmu_kernel(const float* __restrict__ dZc, const float* __restrict__ du,
@@ -852,6 +868,16 @@ void mlr_scalars_fwd(const float* tau, int batch, float eps, float aK, float* sc
 void mlr_scalars_bwd(const float* scal, int batch, float aK, const float* dotOO, const float* trdO,
                      const float* dotHs, float* dtaup, cudaStream_t st) {
   mlr_scalars_bwd_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scal, batch, aK, dotOO, trdO, dotHs, dtaup);
+  note_launch();
+}
+void reduce_splits(const float* partial, int splits, int m, int n, const float* bias, float* y,
+                   cudaStream_t st) {
+  const long long mn = (long long)m * n;
+  reduce_splits_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(partial, splits, mn, n, bias, y);
+  note_launch();
+}
+void colsum(const float* x, int m, int n, float* out, cudaStream_t st) {
+  colsum_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, m, n, out);
   note_launch();
 }
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

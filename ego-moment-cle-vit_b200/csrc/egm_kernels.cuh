@@ -116,6 +116,12 @@ void mlr_scalars_fwd(const float* tau, int batch, float eps, float aK, float* sc
 void mlr_scalars_bwd(const float* scal, int batch, float aK, const float* dotOO, const float* trdO,
                      const float* dotHs, float* dtaup, cudaStream_t st);
 
+// ---- split-K epilogue / bias helpers for the Linear layers
+// y[m,n] = sum_s partial[s,m,n] + bias[n]
+void reduce_splits(const float* partial, int splits, int m, int n, const float* bias, float* y,
+                   cudaStream_t st);
+void colsum(const float* x, int m, int n, float* out, cudaStream_t st);   // out[n] = sum_m x[m,n]
+
 // ---- pooling backward pieces
 // dmu = -(colsum(dZc) + sw*du/(t+eps))
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

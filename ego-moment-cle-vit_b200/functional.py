@@ -335,6 +335,58 @@ def newton_schulz(matrix, num_iterations, eps=1e-5, *, post="divide", precision=
     return _NSFunction.apply(M, int(num_iterations), eps, mode, _prec(precision))
 
 
+# ------------------------------------------------------------------------ linear
+class _LinearFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec):
+        L = _lib.load()
+        M, K = x.shape
+        N = weight.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            y = torch.empty(M, N, device=dev, dtype=torch.float32)
+            state = _ws(L.egm_linear_state_bytes(M, N, K, prec), dev)
+            ws = _ws(L.egm_linear_fwd_workspace(M, N, K, prec), dev)
+            _lib.check(L.egm_linear_fwd(x.data_ptr(), weight.data_ptr(), _p(bias), M, N, K, y.data_ptr(),
+                                        state.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_linear_fwd")
+        ctx.save_for_backward(state)
+        ctx.cfg = (M, N, K, prec, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        L = _lib.load()
+        (state,) = ctx.saved_tensors
+        M, N, K, prec, has_bias = ctx.cfg
+        dev = dy.device
+        dy = dy.contiguous()
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        with torch.cuda.device(dev):
+            dx = torch.empty(M, K, device=dev, dtype=torch.float32) if need_x else None
+            dw = torch.empty(N, K, device=dev, dtype=torch.float32) if need_w else None
+            db = torch.empty(N, device=dev, dtype=torch.float32) if need_b else None
+            ws = _ws(L.egm_linear_bwd_workspace(M, N, K, prec), dev)
+            _lib.check(L.egm_linear_bwd(dy.data_ptr(), state.data_ptr(), M, N, K, _p(dx), _p(dw), _p(db), prec,
+                                        ws.data_ptr(), ws.numel(), _stream(dev)), "egm_linear_bwd")
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, *, precision=None):
+    """F.linear(x, weight, bias) for 2-D x on the tcgen05 engine (split-K over all CTA pairs).
+    In the strict 'fp32_simt' mode this plain GEMM is left to torch (cuBLAS fp32)."""
+    prec = _prec(precision)
+    if prec == _lib.PREC_FP32_SIMT:
+        return torch.nn.functional.linear(x, weight, bias)
+    x = _require_cuda_f32("x", x, 2)
+    w = _require_cuda_f32("weight", weight, 2)
+    if w.shape[1] != x.shape[1]:
+        raise RuntimeError(f"linear: x {tuple(x.shape)} and weight {tuple(w.shape)} do not match")
+    b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
+    return _LinearFunction.apply(x, w, b, prec)
+
+
 # -------------------------------------------------------------------------- triu
 class _TriuFunction(Function):
     @staticmethod

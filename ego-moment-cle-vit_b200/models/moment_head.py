@@ -137,10 +137,21 @@ class MomentHead(nn.Module):
                 M2 = EF.graph_weighted_pool(tokens, graph, eps=self.eps, third_order=False)
             M2_normalized = self.isqrt_cov(M2)
         M2_vec = EF.half_vectorize(M2_normalized)
-        features = [self.second_net(M2_vec)]
+        features = [self._feature_net(self.second_net, M2_vec)]
         if self.use_third_order:
-            features.append(self.third_net(self.tensor_sketch(u)))
+            features.append(self._feature_net(self.third_net, self.tensor_sketch(u)))
         return torch.cat(features, dim=-1)
+
+    @staticmethod
+    def _feature_net(net: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+        """Linear -> BatchNorm1d -> GELU -> Dropout (moment_head.py:186-200). The parameters stay
+        in the reference's nn.Sequential; the Linear's GEMMs (fwd, dx, dW) run on the library's
+        tcgen05 engine, BN/GELU/Dropout on torch."""
+        lin = net[0]
+        x = EF.linear(x, lin.weight, lin.bias)
+        for layer in list(net)[1:]:
+            x = layer(x)
+        return x
 
 
 def test_moment_head():

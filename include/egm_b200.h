@@ -111,6 +111,18 @@ int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G
                 const void* state, int B, int N, int D, int iters, float eps, float* dZ, float* dG,
                 int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
 
+/* ---- Linear layers of second_net / third_net (nn.Linear at moment_head.py:187,196) -------------
+ * y [M,N] = x [M,K] W^T [N,K] + bias [N] on the tcgen05 engine with split-K; state keeps the
+ * operand planes for the backward (dx = dy W, dW = dy^T x, dbias = colsum dy; any may be null).
+ * Tensor-core precision modes only (the strict fp32 mode leaves this GEMM to the caller). */
+size_t egm_linear_state_bytes(int M, int N, int K, int prec);
+size_t egm_linear_fwd_workspace(int M, int N, int K, int prec);
+int egm_linear_fwd(const float* x, const float* W, const float* bias, int M, int N, int K, float* y,
+                   void* state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+size_t egm_linear_bwd_workspace(int M, int N, int K, int prec);
+int egm_linear_bwd(const float* dy, const void* state, int M, int N, int K, float* dx, float* dW,
+                   float* dbias, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+
 /* ---- half-vectorisation (row-major upper triangle incl. diagonal) -------------------------- */
 int egm_triu_pack(const float* O, int B, int D, float* v, egm_stream_t stream);
 int egm_triu_unpack(const float* dv, int B, int D, float* dO, egm_stream_t stream);

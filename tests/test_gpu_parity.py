@@ -463,6 +463,34 @@ def test_training_step_updates_parameters(pkg, dev):
     assert all(not torch.equal(b, q.detach()) for b, q in zip(before, params))
 
 
+@pytest.mark.parametrize("M,K,N", [(256, 768 * 769 // 2, 256), (8, 768 * 769 // 2, 128), (5, 100, 7),
+                                   (33, 1001, 40), (300, 4096, 300)])
+def test_linear_on_the_tensor_core_engine(pkg, dev, M, K, N):
+    """functional.linear == F.linear (second_net / third_net Linear, moment_head.py:187,196):
+    forward with split-K, dx, dW, dbias."""
+    EF = pkg.functional
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    x = torch.randn(M, K, device=dev, generator=g) * 0.02
+    w = torch.randn(N, K, device=dev, generator=g) * (1.0 / K ** 0.5)
+    b = torch.randn(N, device=dev, generator=g)
+    dy = torch.randn(M, N, device=dev, generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (x, w, b)]
+    torch.nn.functional.linear(*ref_in).backward(dy.double())
+    for mode, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        xs, ws_, bs = (t.clone().requires_grad_(True) for t in (x, w, b))
+        with EF.precision(mode):
+            y = EF.linear(xs, ws_, bs)
+            y.backward(dy)
+        yr = torch.nn.functional.linear(*[t.detach() for t in ref_in])
+        assert rel_err(npy(y), npy(yr)) < tol
+        assert rel_err(npy(xs.grad), npy(ref_in[0].grad)) < tol
+        assert rel_err(npy(ws_.grad), npy(ref_in[1].grad)) < tol
+        assert rel_err(npy(bs.grad), npy(ref_in[2].grad)) < 1e-5
+    with EF.precision("fp32"):                      # no bias, no grad for x
+        y2 = EF.linear(x, w.clone().requires_grad_(True))
+        assert rel_err(npy(y2), npy(torch.nn.functional.linear(x.double(), w.double()))) < 1e-4
+
+
 # ------------------------------------------------------- full-size, size-independent checks
 def test_full_size_properties_config2(pkg, dev):
     """B=256, N=197, D=768 (BASELINE config 2): properties that need no oracle."""
