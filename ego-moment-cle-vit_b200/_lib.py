@@ -49,9 +49,15 @@ SIGNATURES = {
     "egm_ns_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _I, _P, _Z, _P]),
     "egm_mlr_state_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "egm_mlr_fwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
-    "egm_mlr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "egm_mlr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_mlr_bwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
-    "egm_mlr_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
+    "egm_mlr_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
+    "egm_mhd_state_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "egm_mhd_fwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
+    "egm_mhd_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "egm_mhd_bwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
+    "egm_mhd_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
+    "egm_rowdot_bias": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "egm_linear_state_bytes": (_Z, [_I, _I, _I, _I]),
     "egm_linear_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_linear_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),

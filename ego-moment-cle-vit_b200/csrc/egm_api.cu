@@ -33,6 +33,172 @@ struct NsState {
   W Y(int k) const { return k == 1 ? T(0) : slot(1 + K + (K - 1) + (k - 2)); }  // k in [1, K-1]
 };
 
+
+// Products of the forward chain given A and T_0 in the state (K >= 2):
+//   Z_1 = T_0 A; k = 1..K-1: T_k = 1.5 I - 0.5 Z_k Y_k, Y_{k+1} = Y_k T_k, Z_{k+1} = T_k Z_k;
+// the last product leaves as  post * Y_{K-1} T_{K-1}  either in fp32 (O) or as the packed upper
+// triangle in bf16 planes (X: the operand of second_net's Linear; lower tiles are not computed).
+int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, const W* X, cudaStream_t st) {
+  const int B = S.B, D = S.D, K = S.K;
+  const long long dd = (long long)D * D;
+  {
+    GemmProblem g;  // Z_1 = T_0 A
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(S.T(0), 0, S.A(), 0, D, prec);
+    out_w(g, S.Z(1), prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  for (int k = 1; k <= K - 1; ++k) {
+    {
+      GemmProblem g;  // T_k = 1.5 I - 0.5 Z_k Y_k
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(S.Z(k), 0, S.Y(k), 0, D, prec);
+      g.alpha = -0.5f; g.beta_eye = 1.5f;
+      out_w(g, S.T(k), prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    if (k < K - 1) {
+      {
+        GemmProblem g;  // Y_{k+1} = Y_k T_k
+        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+        g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+        out_w(g, S.Y(k + 1), prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      {
+        GemmProblem g;  // Z_{k+1} = T_k Z_k
+        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+        g.t[0] = term(S.T(k), 0, S.Z(k), 0, D, prec);
+        out_w(g, S.Z(k + 1), prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+    } else {
+      GemmProblem g;  // O = post * Y_{K-1} T_{K-1}
+      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+      g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+      g.alpha_b = post;
+      if (X) {
+        g.X = w_mat(*X, prec);
+      } else {
+        g.Cf = f32_mat(O, D, D, D, dd);
+      }
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+  }
+  return EGM_OK;
+}
+
+// Where the last backward product (dA) goes: fp32, or planes together with <dA, A>.
+struct NsFinal {
+  float* dA_f32 = nullptr;
+  const W* dA_w = nullptr;
+  float* dot_out = nullptr;   // <dA, A> per image (tensor-core modes, with dA_w)
+  float* dot_ws = nullptr;
+};
+
+// Backward products (K >= 2). buf[0] holds dY_K = post * dO on entry; buf[1..5] are scratch.
+int ns_products_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+  const int B = S.B, D = S.D, K = S.K;
+  const long long dd = (long long)D * D;
+  W dY = buf[0], dYn = buf[1], dZ = buf[2], dZn = buf[3], dP = buf[4], X = buf[5];
+  bool have_dZ = false;
+  for (int k = K - 1; k >= 1; --k) {
+    {
+      GemmProblem g;  // dP = -0.5 (Y_k^T dY [+ dZ Z_k^T])
+      g.M = D; g.N = D; g.batch = B;
+      g.t[0] = term(S.Y(k), 1, dY, 0, D, prec);
+      g.nterms = 1;
+      if (have_dZ) { g.t[1] = term(dZ, 0, S.Z(k), 1, D, prec); g.nterms = 2; }
+      g.alpha = -0.5f;
+      out_w(g, dP, prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    {
+      GemmProblem g;  // dY_k = dY T_k^T + Z_k^T dP
+      g.M = D; g.N = D; g.batch = B; g.nterms = 2;
+      g.t[0] = term(dY, 0, S.T(k), 1, D, prec);
+      g.t[1] = term(S.Z(k), 1, dP, 0, D, prec);
+      out_w(g, dYn, prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    {
+      GemmProblem g;  // dZ_k = [T_k^T dZ +] dP Y_k^T
+      g.M = D; g.N = D; g.batch = B;
+      g.t[0] = term(dP, 0, S.Y(k), 1, D, prec);
+      g.nterms = 1;
+      if (have_dZ) { g.t[1] = term(S.T(k), 1, dZ, 0, D, prec); g.nterms = 2; }
+      out_w(g, dZn, prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    W tmp = dY; dY = dYn; dYn = tmp;
+    tmp = dZ; dZ = dZn; dZn = tmp;
+    have_dZ = true;
+  }
+  // k = 0: Y_1 = T_0, Z_1 = T_0 A, T_0 = 1.5 I - 0.5 A
+  {
+    GemmProblem g;  // X = dT_0 = dY_1 + dZ_1 A^T
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(dZ, 0, S.A(), 1, D, prec);
+    addend_w(g, dY, 1.f, prec);
+    out_w(g, X, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // dA = T_0^T dZ_1 - 0.5 dT_0
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(S.T(0), 1, dZ, 0, D, prec);
+    addend_w(g, X, -0.5f, prec);
+    if (fin.dA_w) {
+      out_w(g, *fin.dA_w, prec);
+      if (fin.dot_out) {
+        g.F = w_mat(S.A(), prec);
+        g.f_planes = 1;
+        g.dot_out = fin.dot_out;
+        g.dot_ws = fin.dot_ws;
+      }
+    } else {
+      g.Cf = f32_mat(fin.dA_f32, D, D, D, dd);
+    }
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  return EGM_OK;
+}
+
+
+// Tail of the pooling backward given V1 = Zc dM^T and V2 = Zc dM:
+//   dZc = Wn V1 + Wn^T V2, dW = V2 Zc^T, then centring / weighted mean / degree normalisation.
+int pool_bwd_tail(const W& Wn, const W& Zc, const W& V1, const W& V2, const float* du, const float* Z,
+                  const float* G, const float* u, const float* vecs, const float* mu, int B, int N, int D,
+                  float eps, float* dZc, float* dW, long long ldW, float* dmu, float* dw, float* ds,
+                  float* dt, float* dZ, float* dG, int prec, cudaStream_t st) {
+  const float* s = vecs;
+  const float* deg = vecs + (size_t)B * N;
+  const float* w = vecs + (size_t)2 * B * N;
+  const float* t = vecs + (size_t)4 * B * N;
+  const float* sw = t + B;
+  {
+    GemmProblem g;  // dZc = Wn V1 + Wn^T V2
+    g.M = N; g.N = D; g.batch = B; g.nterms = 2;
+    g.t[0] = term(Wn, 0, V1, 0, N, prec);
+    g.t[1] = term(Wn, 1, V2, 0, N, prec);
+    g.Cf = f32_mat(dZc, N, D, D, (long long)N * D);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // dW = V2 Zc^T
+    g.M = N; g.N = N; g.batch = B; g.nterms = 1;
+    g.t[0] = term(V2, 0, Zc, 1, D, prec);
+    g.Cf = f32_mat(dW, N, N, ldW, (long long)N * ldW);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  k::pool_bwd_dmu(dZc, du, sw, t, B, N, D, eps, dmu, st);
+  k::pool_bwd_rows(dZc, Z, Zc, w, t, mu, u, du, dmu, B, N, D, eps, dZ, dw, dt, prec, st);
+  k::pool_bwd_ds(dW, ldW, dw, dt, G, s, B, N, ds, st);
+  k::pool_bwd_dG(dW, ldW, dw, dt, s, deg, ds, B, N, eps, dG, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -232,27 +398,8 @@ int egm_pool_bwd(const float* dM2, const float* du, const float* Z, const float*
     out_w(g, V2, prec);
     EGM_CUDA(run_gemm(g, prec, st));
   }
-  {
-    GemmProblem g;  // dZc = Wn V1 + Wn^T V2
-    g.M = N; g.N = D; g.batch = B; g.nterms = 2;
-    g.t[0] = term(Wn, 0, V1, 0, N, prec);
-    g.t[1] = term(Wn, 1, V2, 0, N, prec);
-    g.Cf = f32_mat(dZc, N, D, D, (long long)N * D);
-    EGM_CUDA(run_gemm(g, prec, st));
-  }
-  {
-    GemmProblem g;  // dW = V2 Zc^T
-    g.M = N; g.N = N; g.batch = B; g.nterms = 1;
-    g.t[0] = term(V2, 0, Zc, 1, D, prec);
-    g.Cf = f32_mat(dW, N, N, ldW, (long long)N * ldW);
-    EGM_CUDA(run_gemm(g, prec, st));
-  }
-  k::pool_bwd_dmu(dZc, du, sw, t, B, N, D, eps, dmu, st);
-  k::pool_bwd_rows(dZc, Z, Zc, w, t, mu, u, du, dmu, B, N, D, eps, dZ, dw, dt, prec, st);
-  k::pool_bwd_ds(dW, ldW, dw, dt, G, s, B, N, ds, st);
-  k::pool_bwd_dG(dW, ldW, dw, dt, s, deg, ds, B, N, eps, dG, st);
-  EGM_LAUNCHED();
-  return EGM_OK;
+  return pool_bwd_tail(Wn, Zc, V1, V2, du, Z, G, u, vecs, mu, B, N, D, eps, dZc, dW, ldW, dmu, dw, ds, dt, dZ,
+                       dG, prec, st);
 }
 
 // ============================================================================ NS
@@ -305,48 +452,7 @@ int egm_ns_fwd(const float* M, int B, int D, int iters, float eps, int post_mode
     EGM_LAUNCHED();
     return EGM_OK;
   }
-  // Z_1 = T_0 A
-  {
-    GemmProblem g;
-    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-    g.t[0] = term(S.T(0), 0, A, 0, D, prec);
-    out_w(g, S.Z(1), prec);
-    EGM_CUDA(run_gemm(g, prec, st));
-  }
-  for (int k = 1; k <= K - 1; ++k) {
-    {
-      GemmProblem g;  // T_k = 1.5 I - 0.5 Z_k Y_k
-      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(S.Z(k), 0, S.Y(k), 0, D, prec);
-      g.alpha = -0.5f; g.beta_eye = 1.5f;
-      out_w(g, S.T(k), prec);
-      EGM_CUDA(run_gemm(g, prec, st));
-    }
-    if (k < K - 1) {
-      {
-        GemmProblem g;  // Y_{k+1} = Y_k T_k
-        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-        g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
-        out_w(g, S.Y(k + 1), prec);
-        EGM_CUDA(run_gemm(g, prec, st));
-      }
-      {
-        GemmProblem g;  // Z_{k+1} = T_k Z_k
-        g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-        g.t[0] = term(S.T(k), 0, S.Z(k), 0, D, prec);
-        out_w(g, S.Z(k + 1), prec);
-        EGM_CUDA(run_gemm(g, prec, st));
-      }
-    } else {
-      GemmProblem g;  // O = post * Y_{K-1} T_{K-1}
-      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
-      g.alpha_b = post;
-      g.Cf = f32_mat(O, D, D, D, dd);
-      EGM_CUDA(run_gemm(g, prec, st));
-    }
-  }
-  return EGM_OK;
+  return ns_products_fwd(S, prec, post, O, nullptr, st);
 }
 
 size_t egm_ns_bwd_workspace(int B, int D, int iters, int prec) {
@@ -389,64 +495,180 @@ int egm_ns_bwd(const float* dO, const float* O, const float* M, const float* sca
     k::affine(dO, D, dd, B, D, D, post, -0.5f, 0.f, dAw, 0.f, 0.f, nullptr, PREC_FP32_SIMT, st);
     EGM_LAUNCHED();
   } else {
-    W dY = buf[0], dYn = buf[1], dZ = buf[2], dZn = buf[3], dP = buf[4], X = buf[5];
-    k::affine(dO, D, dd, B, D, D, post, 1.f, 0.f, dY, 0.f, 0.f, nullptr, prec, st);
+    k::affine(dO, D, dd, B, D, D, post, 1.f, 0.f, buf[0], 0.f, 0.f, nullptr, prec, st);
     EGM_LAUNCHED();
-    bool have_dZ = false;
-    for (int k = K - 1; k >= 1; --k) {
-      {
-        GemmProblem g;  // dP = -0.5 (Y_k^T dY [+ dZ Z_k^T])
-        g.M = D; g.N = D; g.batch = B;
-        g.t[0] = term(S.Y(k), 1, dY, 0, D, prec);
-        g.nterms = 1;
-        if (have_dZ) { g.t[1] = term(dZ, 0, S.Z(k), 1, D, prec); g.nterms = 2; }
-        g.alpha = -0.5f;
-        out_w(g, dP, prec);
-        EGM_CUDA(run_gemm(g, prec, st));
-      }
-      {
-        GemmProblem g;  // dY_k = dY T_k^T + Z_k^T dP
-        g.M = D; g.N = D; g.batch = B; g.nterms = 2;
-        g.t[0] = term(dY, 0, S.T(k), 1, D, prec);
-        g.t[1] = term(S.Z(k), 1, dP, 0, D, prec);
-        out_w(g, dYn, prec);
-        EGM_CUDA(run_gemm(g, prec, st));
-      }
-      {
-        GemmProblem g;  // dZ_k = [T_k^T dZ +] dP Y_k^T
-        g.M = D; g.N = D; g.batch = B;
-        g.t[0] = term(dP, 0, S.Y(k), 1, D, prec);
-        g.nterms = 1;
-        if (have_dZ) { g.t[1] = term(S.T(k), 1, dZ, 0, D, prec); g.nterms = 2; }
-        out_w(g, dZn, prec);
-        EGM_CUDA(run_gemm(g, prec, st));
-      }
-      W tmp = dY; dY = dYn; dYn = tmp;
-      tmp = dZ; dZ = dZn; dZn = tmp;
-      have_dZ = true;
-    }
-    // k = 0: Y_1 = T_0, Z_1 = T_0 A, T_0 = 1.5 I - 0.5 A
-    {
-      GemmProblem g;  // X = dT_0 = dY_1 + dZ_1 A^T
-      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(dZ, 0, S.A(), 1, D, prec);
-      addend_w(g, dY, 1.f, prec);
-      out_w(g, X, prec);
-      EGM_CUDA(run_gemm(g, prec, st));
-    }
-    {
-      GemmProblem g;  // dA = T_0^T dZ_1 - 0.5 dT_0
-      g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(S.T(0), 1, dZ, 0, D, prec);
-      addend_w(g, X, -0.5f, prec);
-      g.Cf = f32_mat(dA, D, D, D, dd);
-      EGM_CUDA(run_gemm(g, prec, st));
-    }
+    NsFinal fin;
+    fin.dA_f32 = dA;
+    const int rc = ns_products_bwd(S, prec, buf, fin, st);
+    if (rc != EGM_OK) return rc;
   }
   // A = inv * M with inv = 1/(tau+eps):  dM = inv dA + (d tau) I,
   //   d tau = coef_tau <dO,O> inv - <dA,M> inv^2
   k::batch_dot(dA, M, B, dd, dotA, st);
   k::ns_bwd_finish(dA, inv, dotO, dotA, coef_tau, B, D, dM, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+// ============================================================ fused dense moment head
+// pool -> trace normalisation -> Newton-Schulz (D x D) -> packed half-vector, with every
+// intermediate kept in the GEMM engine's operand format: no fp32 M2 / O / dO / dM round trips.
+//   tau = tr(Zc^T Wn Zc) = <Zc, U>      (a by-product of the U = Wn Zc product)
+//   A = Zc^T U / (tau+eps) and T_0 = 1.5 I - 0.5 A leave the same accumulator
+//   the last product writes post * Y_K as the packed upper triangle = operand of the Linear
+// Backward: dY_K = post * unpack(dv); <dO,O> is supplied by the caller (for y = x W^T + b it is
+// <dy, y - b>); <dA,A> is a by-product of the last product; dM = inv dA + dtau I is never formed:
+// V1 = Zc dM^T = inv Zc dA^T + dtau Zc, V2 = Zc dM = inv Zc dA + dtau Zc.
+size_t egm_mhd_state_bytes(int B, int N, int D, int iters, int prec) {
+  return egm_pool_state_bytes(B, N, D, prec) + egm_ns_state_bytes(B, D, iters, prec) + 256;
+}
+size_t egm_mhd_fwd_workspace(int B, int N, int D, int iters, int prec) {
+  (void)iters; (void)prec;
+  return pad256(w_bytes(B, N, D)) + pad256((size_t)B * 4) +
+         pad256((size_t)B * ((N + 127) / 128 + 1) * 4 * ((D + 255) / 256) * 4) + 2048;
+}
+
+int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps,
+                void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
+              "egm_mhd_fwd: tensor-core precision modes only (got %d)", prec);
+  EGM_REQUIRE(Z && G && x_planes && vecs && mu && scal && state, EGM_ERR_ARG, "egm_mhd_fwd: null pointer");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && iters >= 2 && iters <= 64, EGM_ERR_ARG,
+              "egm_mhd_fwd: bad sizes (needs iters >= 2)");
+  const int K = iters;
+  const size_t pool_bytes = pad256(egm_pool_state_bytes(B, N, D, prec));
+  Arena sa(state, pool_bytes);
+  const W Wn = make_w(sa.take(w_bytes(B, N, N)), B, N, N);
+  const W Zc = make_w(sa.take(w_bytes(B, N, D)), B, N, D);
+  NsState S(static_cast<uint8_t*>(state) + pool_bytes, B, D, K);
+  Arena ar(ws, ws_bytes);
+  const W U = make_w(ar.take(w_bytes(B, N, D)), B, N, D);
+  float* tau = static_cast<float*>(ar.take((size_t)B * 4));
+  GemmProblem gu;  // U = Wn Zc, tau = <U, Zc>
+  gu.M = N; gu.N = D; gu.batch = B; gu.nterms = 1;
+  gu.t[0] = term(Wn, 0, Zc, 0, N, prec);
+  out_w(gu, U, prec);
+  gu.F = w_mat(Zc, prec);
+  gu.f_planes = 1;
+  gu.dot_out = tau;
+  float* dot_ws = static_cast<float*>(ar.take(gemm_tc_dot_ws_floats(gu) * 4));
+  gu.dot_ws = dot_ws;
+  EGM_REQUIRE(U.base && tau && dot_ws, EGM_ERR_WORKSPACE, "egm_mhd_fwd: workspace %zu < %zu", ws_bytes,
+              egm_mhd_fwd_workspace(B, N, D, iters, prec));
+  PoolVecs pv(vecs, B, N);
+  k::degree(G, B, N, eps, pv.deg, pv.s, st);
+  k::weight(G, pv.s, B, N, Wn, pv.w, pv.wdiag, prec, st);
+  k::mean_center(Z, pv.w, pv.wdiag, B, N, D, eps, pv.t, pv.sw, mu, u, Zc, prec, st);
+  EGM_LAUNCHED();
+  EGM_CUDA(run_gemm(gu, prec, st));
+  k::mh_scalars_fwd(tau, B, eps, scal, st);
+  EGM_LAUNCHED();
+  const float* inv = scal + B;
+  const float* post = scal + 2 * B;
+  {
+    GemmProblem g;  // A = inv Zc^T U ; T_0 = 1.5 I - 0.5 A
+    g.M = D; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 1, U, 0, N, prec);
+    g.alpha_b = inv;
+    out_w(g, S.A(), prec);
+    g.Cp2 = w_mat(S.T(0), prec);
+    g.c2_scale = -0.5f; g.c2_eye = 1.5f;
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  const long long L = (long long)D * (D + 1) / 2;
+  W X;
+  X.base = x_planes; X.rows = B; X.cols = (int)L; X.ld = w_ld((int)L); X.batch = 1;
+  return ns_products_fwd(S, prec, post, nullptr, &X, st);
+}
+
+size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec) {
+  (void)iters; (void)prec;
+  return 7 * pad256(w_bytes(B, D, D)) + 2 * pad256(w_bytes(B, N, D)) + pad256((size_t)B * N * D * 4) +
+         pad256((size_t)B * N * egm_gpf_ldr(N) * 4) + pad256((size_t)B * D * 4) +
+         3 * pad256((size_t)B * N * 4) + 2 * pad256((size_t)B * 4) +
+         pad256((size_t)B * 8 * 4 * ((D + 255) / 256) * ((D + 255) / 256)) + 4096;
+}
+
+int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float* Z, const float* G,
+                const float* u, const float* vecs, const float* mu, const float* scal, const void* state,
+                int B, int N, int D, int iters, float eps, float* dZ, float* dG, int prec, void* ws,
+                size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
+              "egm_mhd_bwd: tensor-core precision modes only (got %d)", prec);
+  EGM_REQUIRE(dv && dotO && Z && G && vecs && mu && scal && state && dZ && dG, EGM_ERR_ARG,
+              "egm_mhd_bwd: null pointer");
+  EGM_REQUIRE(!du || u, EGM_ERR_ARG, "egm_mhd_bwd: du given without u");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && iters >= 2 && iters <= 64, EGM_ERR_ARG, "egm_mhd_bwd: bad sizes");
+  const int K = iters;
+  const size_t pool_bytes = pad256(egm_pool_state_bytes(B, N, D, prec));
+  Arena sa(const_cast<void*>(state), pool_bytes);
+  const W Wn = make_w(sa.take(w_bytes(B, N, N)), B, N, N);
+  const W Zc = make_w(sa.take(w_bytes(B, N, D)), B, N, D);
+  NsState S(static_cast<uint8_t*>(const_cast<void*>(state)) + pool_bytes, B, D, K);
+  Arena ar(ws, ws_bytes);
+  W buf[6];
+  for (int i = 0; i < 6; ++i) buf[i] = make_w(ar.take(w_bytes(B, D, D)), B, D, D);
+  const W dAw = make_w(ar.take(w_bytes(B, D, D)), B, D, D);
+  const W V1 = make_w(ar.take(w_bytes(B, N, D)), B, N, D), V2 = make_w(ar.take(w_bytes(B, N, D)), B, N, D);
+  float* dZc = static_cast<float*>(ar.take((size_t)B * N * D * 4));
+  const long long ldW = egm_gpf_ldr(N);
+  float* dW = static_cast<float*>(ar.take((size_t)B * N * ldW * 4));
+  float* dmu = static_cast<float*>(ar.take((size_t)B * D * 4));
+  float* dw = static_cast<float*>(ar.take((size_t)B * N * 4));
+  float* ds = static_cast<float*>(ar.take((size_t)B * N * 4));
+  float* dt = static_cast<float*>(ar.take((size_t)B * N * 4));
+  float* dotA = static_cast<float*>(ar.take((size_t)B * 4));
+  float* dtau = static_cast<float*>(ar.take((size_t)B * 4));
+  const int tl = (D + 255) / 256;
+  float* dot_ws = static_cast<float*>(ar.take((size_t)B * 8 * 4 * tl * tl));
+  EGM_REQUIRE(buf[5].base && dAw.base && V1.base && V2.base && dZc && dW && dmu && dw && ds && dt && dotA &&
+                  dtau && dot_ws,
+              EGM_ERR_WORKSPACE, "egm_mhd_bwd: workspace %zu < %zu", ws_bytes,
+              egm_mhd_bwd_workspace(B, N, D, iters, prec));
+  const float* inv = scal + B;
+  const float* post = scal + 2 * B;
+  const long long L = (long long)D * (D + 1) / 2;
+  k::triu_unpack_planes(dv, L, B, D, post, buf[0], nullptr, prec, st);   // dY_K = post * dO
+  EGM_LAUNCHED();
+  NsFinal fin;
+  fin.dA_w = &dAw;
+  fin.dot_out = dotA;
+  fin.dot_ws = dot_ws;
+  const int rc = ns_products_bwd(S, prec, buf, fin, st);
+  if (rc != EGM_OK) return rc;
+  k::mh_dtau(scal, B, dotO, dotA, dtau, st);
+  EGM_LAUNCHED();
+  {
+    GemmProblem g;  // V1 = Zc dM^T = inv Zc dA^T + dtau Zc
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 0, dAw, 1, D, prec);
+    g.alpha_b = inv;
+    addend_w(g, Zc, 1.f, prec);
+    g.gamma_b = dtau;
+    out_w(g, V1, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  {
+    GemmProblem g;  // V2 = Zc dM = inv Zc dA + dtau Zc
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 0, dAw, 0, D, prec);
+    g.alpha_b = inv;
+    addend_w(g, Zc, 1.f, prec);
+    g.gamma_b = dtau;
+    out_w(g, V2, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  return pool_bwd_tail(Wn, Zc, V1, V2, du, Z, G, u, vecs, mu, B, N, D, eps, dZc, dW, ldW, dmu, dw, ds, dt,
+                       dZ, dG, prec, st);
+}
+
+int egm_rowdot_bias(const float* dy, const float* y, const float* bias, int B, int n, float* out,
+                    egm_stream_t stream) {
+  EGM_REQUIRE(dy && y && out && B > 0 && n > 0, EGM_ERR_ARG, "egm_rowdot_bias: bad argument");
+  k::rowdot_bias(dy, y, bias, B, n, out, static_cast<cudaStream_t>(stream));
   EGM_LAUNCHED();
   return EGM_OK;
 }
@@ -569,7 +791,7 @@ int egm_linear_fwd(const float* x, const float* Wt, const float* bias, int M, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
               "egm_linear_fwd: tensor-core precision modes only (got %d)", prec);
-  EGM_REQUIRE(x && Wt && y && state && M > 0 && N > 0 && K > 0, EGM_ERR_ARG, "egm_linear_fwd: bad argument");
+  EGM_REQUIRE(Wt && y && state && M > 0 && N > 0 && K > 0, EGM_ERR_ARG, "egm_linear_fwd: bad argument");
   Arena sa(state, egm_linear_state_bytes(M, N, K, prec));
   const W Xw = make_w(sa.take(w_bytes(1, M, K)), 1, M, K);
   const W Ww = make_w(sa.take(w_bytes(1, N, K)), 1, N, K);
@@ -577,7 +799,8 @@ int egm_linear_fwd(const float* x, const float* Wt, const float* bias, int M, in
   Arena ar(ws, ws_bytes);
   float* partial = static_cast<float*>(ar.take((size_t)S * M * N * 4));
   EGM_REQUIRE(partial, EGM_ERR_WORKSPACE, "egm_linear_fwd: workspace too small");
-  k::affine(x, K, (long long)M * K, 1, M, K, nullptr, 1.f, 0.f, Xw, 0.f, 0.f, nullptr, prec, st);
+  // x == NULL: the producer (egm_mhd_fwd / egm_mlr_fwd) already wrote the operand planes into `state`
+  if (x) k::affine(x, K, (long long)M * K, 1, M, K, nullptr, 1.f, 0.f, Xw, 0.f, 0.f, nullptr, prec, st);
   k::affine(Wt, K, (long long)N * K, 1, N, K, nullptr, 1.f, 0.f, Ww, 0.f, 0.f, nullptr, prec, st);
   EGM_LAUNCHED();
   GemmProblem g;

@@ -58,7 +58,25 @@ struct GemmProblem {
   int e_planes = 0;
   Mat Cp;            // optional output as bf16 planes (p0 == nullptr: absent)
   Mat Cf;            // optional output as fp32       (p0 == nullptr: absent)
+  // ---- tcgen05 engine only -------------------------------------------------------------
+  // second plane output of the same accumulator: Cp2 = c2_scale * C + c2_eye * I
+  // (e.g. A = M/tau and T_0 = 1.5 I - 0.5 A from one product)
+  Mat Cp2;
+  float c2_scale = 0.f, c2_eye = 0.f;
+  // dot_out[b] = <C[b], F[b]> (deterministic: per-warp partials in dot_ws, then a fixed-order
+  // reduction). dot_ws needs gemm_tc_dot_ws_floats(g) floats.
+  Mat F;
+  int f_planes = 0;
+  float* dot_out = nullptr;
+  float* dot_ws = nullptr;
+  // packed upper triangle (row-major, diagonal included) of the square result as bf16 planes:
+  // X.p0/p1[b * X.ld + i*N - i(i-1)/2 + j - i] = C[b][i][j], j >= i. Tiles strictly below the
+  // diagonal are not computed at all. Excludes Cp / Cp2.
+  Mat X;
 };
+
+// floats of workspace `dot_ws` must provide for problem g (0 when no dot is requested)
+size_t gemm_tc_dot_ws_floats(const GemmProblem& g);
 
 // Returns cudaSuccess or the launch error. No allocation, no synchronisation.
 cudaError_t gemm_tc(const GemmProblem& g, int npass /*1 or 3*/, cudaStream_t stream);

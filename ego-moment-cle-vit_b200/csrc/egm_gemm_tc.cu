@@ -52,11 +52,15 @@ constexpr int kEpiBytes = 4 * kEpiWarpBytes;
 struct alignas(64) TcParams {
   CUtensorMap tm[2][4];  // [term][A_hi, A_lo, B_hi, B_lo]
   CUtensorMap tmC[3];    // TMA-store maps: C_hi, C_lo (bf16, 64B swizzle), C_f32 (128B swizzle)
-  int tma_cp, tma_cf;    // which outputs leave through TMA stores
+  CUtensorMap tmC2[2];   // TMA-store maps of the secondary plane output
+  int tma_cp, tma_cf, tma_c2;  // which outputs leave through TMA stores
   int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
   int tiles_m, tiles_n;
+  int tiles_per_img;     // tiles_m * tiles_n, or the upper-triangular subset (triu_tiles)
+  int triu_tiles;        // enumerate only tiles that touch j >= i
+  int tile_rows;         // rows of one tile: BM (1-CTA kernel) or 2*BM (pair kernel)
   float alpha, beta_eye, gamma;
   const float* alpha_b;
   const float* beta_b;
@@ -70,6 +74,21 @@ struct alignas(64) TcParams {
   long long ldCp, bsCp;
   float* Cf;
   long long ldCf, bsCf;
+  // secondary plane output  c2_scale * C + c2_eye * I
+  __nv_bfloat16* C2_hi;
+  __nv_bfloat16* C2_lo;
+  long long ldC2, bsC2;
+  float c2_scale, c2_eye;
+  // <C, F> partials
+  const void* F0;
+  const void* F1;
+  long long ldF, bsF;
+  int f_mode;  // 0 none, 1 bf16 planes, 2 fp32
+  float* dot_ws;
+  // packed upper triangle as planes
+  __nv_bfloat16* X_hi;
+  __nv_bfloat16* X_lo;
+  long long ldX;
 };
 
 template <int NPASS>
@@ -89,133 +108,211 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
          (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
 
+// tile index within one image -> (row tile, column tile). With triu_tiles only the tiles that
+// contain at least one element on or above the diagonal are enumerated (row-tile major).
+__device__ __forceinline__ void tile_coords(const TcParams& p, int r, int& tm, int& tn) {
+  if (!p.triu_tiles) {
+    tm = r / p.tiles_n;
+    tn = r - tm * p.tiles_n;
+    return;
+  }
+  tm = 0;
+  for (;;) {
+    const int first = (tm * p.tile_rows) / BN;
+    const int cnt = p.tiles_n - first;
+    if (r < cnt) { tn = first + r; return; }
+    r -= cnt;
+    ++tm;
+  }
+}
+
+// 32 consecutive elements of row `row` (columns col0..col0+31) of a batched matrix stored as
+// bf16 hi(/lo) planes (mode 1) or fp32 (mode 2); columns >= ncols read as zero.
+__device__ __forceinline__ void load_chunk(const void* P0, const void* P1, int mode, long long ld,
+                                           long long bs, int b, int row, int col0, int ncols,
+                                           float (&e)[32]) {
+  const bool full = (col0 + 32 <= ncols);
+  if (mode == 1) {
+    const __nv_bfloat16* eh = static_cast<const __nv_bfloat16*>(P0) + b * bs + (long long)row * ld + col0;
+    const __nv_bfloat16* el =
+        P1 ? static_cast<const __nv_bfloat16*>(P1) + b * bs + (long long)row * ld + col0 : nullptr;
+    if (full && (ld & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(eh) + j);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          e[j * 8 + 2 * w] = __uint_as_float(hw[w] << 16);
+          e[j * 8 + 2 * w + 1] = __uint_as_float(hw[w] & 0xFFFF0000u);
+        }
+        if (el) {
+          const uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
+          const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            e[j * 8 + 2 * w] += __uint_as_float(lw[w] << 16);
+            e[j * 8 + 2 * w + 1] += __uint_as_float(lw[w] & 0xFFFF0000u);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = 0.f;
+        if (col0 + j < ncols) {
+          x = __bfloat162float(eh[j]);
+          if (el) x += __bfloat162float(el[j]);
+        }
+        e[j] = x;
+      }
+    }
+  } else {
+    const float* ef = static_cast<const float*>(P0) + b * bs + (long long)row * ld + col0;
+    if (full && (ld & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(ef) + j);
+        e[4 * j] = x.x; e[4 * j + 1] = x.y; e[4 * j + 2] = x.z; e[4 * j + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e[j] = (col0 + j < ncols) ? ef[j] : 0.f;
+    }
+  }
+}
+
+// one lane's row of a 32 x 32 chunk -> bf16 hi/lo staging slot (rows of 64 B, 64B swizzle)
+__device__ __forceinline__ void stage_planes(uint32_t buf, int lane, const float (&o)[32], bool has_lo) {
+  const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(o[j * 8 + 2 * w], h0, l0);
+      split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
+      hw[w] = pack2(h0, h1);
+      lw[w] = pack2(l0, l1);
+    }
+    const uint32_t off = lane * 64 + ((j ^ sw) << 4);
+    ptx::sts128(buf + off, hw[0], hw[1], hw[2], hw[3]);
+    if (has_lo) ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// Plane output of one chunk: TMA store through the staging slot when the layout allows it
+// (full-line writes, no LSU traffic, ragged edges clipped by the tensor map), else scalar.
+__device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, const CUtensorMap* tmh,
+                                             const CUtensorMap* tml, __nv_bfloat16* hi,
+                                             __nv_bfloat16* lo, long long ld, long long bs, int b,
+                                             int row, int row0, int col0, int ncols, bool row_ok,
+                                             int lane, uint32_t stage_smem, int& slot) {
+  if (tma) {
+    const uint32_t buf = stage_smem + slot * 4096;
+    if (lane == 0) ptx::bulk_wait_read<1>();   // the store that used this slot has drained
+    __syncwarp();
+    stage_planes(buf, lane, o, lo != nullptr);
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_3d(tmh, buf, col0, row0, b);
+      if (lo) ptx::tma_store_3d(tml, buf + 2048, col0, row0, b);
+      ptx::bulk_commit();
+    }
+    slot ^= 1;
+  } else if (row_ok) {
+    __nv_bfloat16* ch = hi + b * bs + (long long)row * ld + col0;
+    __nv_bfloat16* cl = lo ? lo + b * bs + (long long)row * ld + col0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < ncols) {
+        __nv_bfloat16 h, l;
+        split_bf16(o[j], h, l);
+        ch[j] = h;
+        if (cl) cl[j] = l;
+      }
+  }
+}
+
 // Epilogue of one accumulator tile for one warp: TMEM -> registers -> alpha*acc + beta*I +
-// gamma*E -> bf16 hi/lo planes and/or fp32. `t_addr` addresses this warp's 32 TMEM lanes,
-// `row0` is the warp's first output row, `n0` the first output column of the 256-wide tile.
-// Outputs leave through TMA stores whenever their layout allows it: each lane writes its row
-// of the 32 x 32 chunk into a swizzled (bank-conflict-free) staging slot and one lane issues
-// cp.async.bulk.tensor - full-line writes, no LSU traffic, ragged edges clipped by the
-// tensor map. Two 4 KiB slots per warp alternate (`slot`), so the store of chunk c overlaps
-// the TMEM read of chunk c+1.
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr, int b, int row0,
-                                              int lane, int n0, uint32_t stage_smem, int& slot) {
+// gamma*E -> bf16 hi/lo planes and/or fp32 (+ optional secondary planes, <C,F> partial, packed
+// upper triangle). `t_addr` addresses this warp's 32 TMEM lanes, `row0` is the warp's first
+// output row, `n0` the first output column of the 256-wide tile. Two 4 KiB staging slots per
+// warp alternate (`slot`), so the store of chunk c overlaps the TMEM read of chunk c+1.
+// Returns this lane's share of <C, F>.
+__device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_addr, int b, int row0,
+                                               int lane, int n0, uint32_t stage_smem, int& slot) {
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
   const float beta = p.beta_eye * (p.beta_b ? __ldg(p.beta_b + b) : 1.f);
   const float gamma = p.gamma * (p.gamma_b ? __ldg(p.gamma_b + b) : 1.f);
+  float dsum = 0.f;
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     const int col0 = n0 + c * 32;
     if (col0 >= p.N) break;  // warp-uniform
+    if (p.X_hi && col0 + 31 < row0) continue;  // chunk entirely below the diagonal (warp-uniform)
     uint32_t v[32];
     ptx::tmem_ld_32x32(t_addr + c * 32, v);
     ptx::tmem_ld_wait();
     float o[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
-    if (beta != 0.f) {
-      const int d = row - col0;
-      if (d >= 0 && d < 32) {
+    const int d = row - col0;  // diagonal position inside this chunk, if any
+    if (beta != 0.f && d >= 0 && d < 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j == d) o[j] += beta;
-      }
+      for (int j = 0; j < 32; ++j)
+        if (j == d) o[j] += beta;
     }
-    const bool full = (col0 + 32 <= p.N);
-    if (p.e_mode == 1 && row_ok) {
-      const __nv_bfloat16* eh =
-          static_cast<const __nv_bfloat16*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
-      const __nv_bfloat16* el =
-          p.E1 ? static_cast<const __nv_bfloat16*>(p.E1) + b * p.bsE + (long long)row * p.ldE + col0
-               : nullptr;
-      if (full && (p.ldE & 7) == 0) {
+    if (p.e_mode && row_ok) {
+      float e[32];
+      load_chunk(p.E0, p.E1, p.e_mode, p.ldE, p.bsE, b, row, col0, p.N, e);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 h = __ldg(reinterpret_cast<const uint4*>(eh) + j);
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            o[j * 8 + 2 * w] += gamma * __uint_as_float(hw[w] << 16);
-            o[j * 8 + 2 * w + 1] += gamma * __uint_as_float(hw[w] & 0xFFFF0000u);
-          }
-          if (el) {
-            uint4 l = __ldg(reinterpret_cast<const uint4*>(el) + j);
-            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              o[j * 8 + 2 * w] += gamma * __uint_as_float(lw[w] << 16);
-              o[j * 8 + 2 * w + 1] += gamma * __uint_as_float(lw[w] & 0xFFFF0000u);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) {
-            float e = __bfloat162float(eh[j]);
-            if (el) e += __bfloat162float(el[j]);
-            o[j] += gamma * e;
-          }
-      }
-    } else if (p.e_mode == 2 && row_ok) {
-      const float* ef = static_cast<const float*>(p.E0) + b * p.bsE + (long long)row * p.ldE + col0;
-      if (full && (p.ldE & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 e = __ldg(reinterpret_cast<const float4*>(ef) + j);
-          o[4 * j] += gamma * e.x;
-          o[4 * j + 1] += gamma * e.y;
-          o[4 * j + 2] += gamma * e.z;
-          o[4 * j + 3] += gamma * e.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) o[j] += gamma * ef[j];
-      }
+      for (int j = 0; j < 32; ++j) o[j] = fmaf(gamma, e[j], o[j]);
     }
-    if (p.Cp_hi) {
-      if (p.tma_cp) {
-        const uint32_t buf = stage_smem + slot * 4096;
-        if (lane == 0) ptx::bulk_wait_read<1>();   // the store that used this slot has drained
-        __syncwarp();
-        const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
+    if (p.f_mode && row_ok) {
+      float f[32];
+      load_chunk(p.F0, p.F1, p.f_mode, p.ldF, p.bsF, b, row, col0, p.N, f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t hw[4], lw[4];
+      for (int j = 0; j < 32; ++j) dsum = fmaf(o[j], f[j], dsum);
+    }
+    if (p.Cp_hi)
+      store_planes(o, p.tma_cp != 0, &p.tmC[0], &p.tmC[1], p.Cp_hi, p.Cp_lo, p.ldCp, p.bsCp, b, row, row0,
+                   col0, p.N, row_ok, lane, stage_smem, slot);
+    if (p.C2_hi) {
+      float o2[32];
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(o[j * 8 + 2 * w], h0, l0);
-            split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
-            hw[w] = pack2(h0, h1);
-            lw[w] = pack2(l0, l1);
-          }
-          const uint32_t off = lane * 64 + ((j ^ sw) << 4);
-          ptx::sts128(buf + off, hw[0], hw[1], hw[2], hw[3]);
-          if (p.Cp_lo) ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_3d(&p.tmC[0], buf, col0, row0, b);
-          if (p.Cp_lo) ptx::tma_store_3d(&p.tmC[1], buf + 2048, col0, row0, b);
-          ptx::bulk_commit();
-        }
-        slot ^= 1;
-      } else if (row_ok) {
-        __nv_bfloat16* ch = p.Cp_hi + b * p.bsCp + (long long)row * p.ldCp + col0;
-        __nv_bfloat16* cl = p.Cp_lo ? p.Cp_lo + b * p.bsCp + (long long)row * p.ldCp + col0 : nullptr;
+      for (int j = 0; j < 32; ++j) o2[j] = p.c2_scale * o[j];
+      if (p.c2_eye != 0.f && d >= 0 && d < 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) {
-            __nv_bfloat16 h, l;
-            split_bf16(o[j], h, l);
-            ch[j] = h;
-            if (cl) cl[j] = l;
-          }
+          if (j == d) o2[j] += p.c2_eye;
       }
+      store_planes(o2, p.tma_c2 != 0, &p.tmC2[0], &p.tmC2[1], p.C2_hi, p.C2_lo, p.ldC2, p.bsC2, b, row,
+                   row0, col0, p.N, row_ok, lane, stage_smem, slot);
+    }
+    if (p.X_hi) {
+      // packed upper triangle: stage the chunk, then every row leaves as one contiguous run
+      const uint32_t buf = stage_smem + slot * 4096;
+      __syncwarp();
+      stage_planes(buf, lane, o, p.X_lo != nullptr);
+      __syncwarp();
+      const int j = col0 + lane;
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int i = row0 + r;
+        if (i >= p.M) break;  // warp-uniform
+        if (j >= i && j < p.N) {
+          const uint32_t off = r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2;
+          const long long idx = (long long)b * p.ldX + (long long)i * p.N - (long long)i * (i - 1) / 2 + (j - i);
+          p.X_hi[idx] = __ushort_as_bfloat16(ptx::lds16(buf + off));
+          if (p.X_lo) p.X_lo[idx] = __ushort_as_bfloat16(ptx::lds16(buf + 2048 + off));
+        }
+      }
+      slot ^= 1;
     }
     if (p.Cf) {
       if (p.tma_cf) {
@@ -237,7 +334,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
         slot ^= 1;
       } else if (row_ok) {
         float* cf = p.Cf + b * p.bsCf + (long long)row * p.ldCf + col0;
-        if (full && (p.ldCf & 3) == 0) {
+        if (col0 + 32 <= p.N && (p.ldCf & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             reinterpret_cast<float4*>(cf)[j] =
@@ -250,6 +347,27 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t t_addr
       }
     }
   }
+  return dsum;
+}
+
+// this warp's <C,F> partial of one tile -> dot_ws[(b * tiles_per_img + r) * nwarps + w]
+__device__ __forceinline__ void write_dot_partial(const TcParams& p, float dsum, int lane, long long slot_idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if (lane == 0) p.dot_ws[slot_idx] = dsum;
+}
+
+// dot_out[b] = sum of the image's partials, fixed order (one warp per image)
+__global__ void dot_reduce_kernel(const float* __restrict__ ws, int per_img, int batch,
+                                  float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  for (int i = lane; i < per_img; i += 32) a += ws[(long long)b * per_img + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[b] = a;
 }
 
 template <int NPASS>
@@ -300,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int tiles_per_img = p.tiles_m * p.tiles_n;
+  const int tiles_per_img = p.tiles_per_img;
   const int ntiles = tiles_per_img * p.batch;
 
   if (warp == 0) {
@@ -311,8 +429,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
-        const int m0 = (r / p.tiles_n) * BM;
-        const int n0 = (r % p.tiles_n) * BN;
+        int tm, tn;
+        tile_coords(p, r, tm, tn);
+        const int m0 = tm * BM;
+        const int n0 = tn * BN;
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
           const int nkb_all = (p.K[t] + BK - 1) / BK;
@@ -409,12 +529,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
-      const int m0 = (r / p.tiles_n) * BM;
-      const int n0 = (r % p.tiles_n) * BN;
+      int tm, tn;
+      tile_coords(p, r, tm, tn);
+      const int m0 = tm * BM;
+      const int n0 = tn * BN;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b, m0 + q * 32, lane,
-                    n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
+      const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
+                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
+      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * 4 + q);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -497,7 +620,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int tiles_per_img = p.tiles_m * p.tiles_n;       // tiles_m counts 256-row tiles here
+  const int tiles_per_img = p.tiles_per_img;             // tiles_m counts 256-row tiles here
   const int ntiles = tiles_per_img * p.batch;
   const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
@@ -510,8 +633,10 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
-        const int m0 = (r / p.tiles_n) * (2 * BM) + rank * BM;        // this CTA's 128 rows
-        const int n0 = (r % p.tiles_n) * BN + rank * (BN / 2);        // this CTA's 128 columns of B
+        int tm, tn;
+        tile_coords(p, r, tm, tn);
+        const int m0 = tm * (2 * BM) + rank * BM;        // this CTA's 128 rows
+        const int n0 = tn * BN + rank * (BN / 2);        // this CTA's 128 columns of B
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
           const int nkb_all = (p.K[t] + BK - 1) / BK;
@@ -609,12 +734,15 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
-      const int m0 = (r / p.tiles_n) * (2 * BM) + rank * BM;
-      const int n0 = (r % p.tiles_n) * BN;
+      int tm, tn;
+      tile_coords(p, r, tm, tn);
+      const int m0 = tm * (2 * BM) + rank * BM;
+      const int n0 = tn * BN;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b, m0 + q * 32, lane,
-                    n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
+      const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
+                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
+      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * 8 + rank * 4 + q);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -726,7 +854,7 @@ cudaError_t launch(const TcParams& p, cudaStream_t stream) {
   int sms = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  const long long ntiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+  const long long ntiles = (long long)p.tiles_per_img * p.batch;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   gemm_tc_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
   note_launch();
@@ -749,7 +877,7 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   int sms = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  const long long ntiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+  const long long ntiles = (long long)p.tiles_per_img * p.batch;
   const long long pairs = sms / 2;
   const int grid = 2 * (int)(ntiles < pairs ? ntiles : pairs);
   gemm_tc2_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
@@ -777,6 +905,25 @@ bool gemm_tc_supported(const GemmProblem& g, int npass) {
   return g.M > 0 && g.N > 0 && g.batch > 0;
 }
 
+// number of tiles per image and (for triu_tiles) the upper-triangular subset
+static int count_tiles(int tiles_m, int tiles_n, int tile_rows, bool triu) {
+  if (!triu) return tiles_m * tiles_n;
+  int n = 0;
+  for (int tm = 0; tm < tiles_m; ++tm) {
+    const int first = (tm * tile_rows) / BN;
+    if (first < tiles_n) n += tiles_n - first;
+  }
+  return n;
+}
+
+size_t gemm_tc_dot_ws_floats(const GemmProblem& g) {
+  if (!g.dot_out) return 0;
+  const int ctas = tc_ctas();
+  const int tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
+  const int tiles_n = (g.N + BN - 1) / BN;
+  return (size_t)g.batch * tiles_m * tiles_n * 4 * ctas;
+}
+
 cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   if (npass != 1 && npass != 3) {
     set_error("gemm_tc: npass must be 1 or 3");
@@ -796,6 +943,18 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   const int ctas = tc_ctas();
   p.tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   p.tiles_n = (g.N + BN - 1) / BN;
+  p.tile_rows = ctas * BM;
+  p.triu_tiles = g.X.p0 ? 1 : 0;
+  p.tiles_per_img = count_tiles(p.tiles_m, p.tiles_n, p.tile_rows, p.triu_tiles != 0);
+  if (g.X.p0) {
+    if (g.M != g.N || g.Cp.p0 || g.Cp2.p0 || g.split_k > 1 || g.dot_out) {
+      set_error("gemm_tc: the packed-triangle output needs a square result and excludes Cp/Cp2/split-K/dot");
+      return cudaErrorInvalidValue;
+    }
+    p.X_hi = static_cast<__nv_bfloat16*>(g.X.p0);
+    p.X_lo = static_cast<__nv_bfloat16*>(g.X.p1);
+    p.ldX = g.X.ld;
+  }
   for (int t = 0; t < g.nterms; ++t) {
     const GemmTerm& gt = g.t[t];
     p.K[t] = gt.K;
@@ -820,8 +979,8 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   if (g.split_k > 1) {
     // K-slices of one product; slice s writes partial sums to output batch index s
     const int nkb = (g.t[0].K + BK - 1) / BK;
-    if (g.nterms != 1 || g.batch != 1 || g.split_k > nkb || g.Cp.p0 || !g.Cf.p0) {
-      set_error("gemm_tc: split-K needs one term, batch 1, an fp32 output and split_k <= K/64");
+    if (g.nterms != 1 || g.batch != 1 || g.split_k > nkb || g.Cp.p0 || g.Cp2.p0 || g.dot_out || !g.Cf.p0) {
+      set_error("gemm_tc: split-K needs one term, batch 1, an fp32 output only and split_k <= K/64");
       return cudaErrorInvalidValue;
     }
     p.splits = g.split_k;
@@ -840,14 +999,28 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     p.bsE = g.E.bstride;
     p.e_mode = g.e_planes ? 1 : 2;
   }
+  if (g.dot_out) {
+    if (!g.F.p0 || !g.dot_ws) {
+      set_error("gemm_tc: dot_out needs F and dot_ws");
+      return cudaErrorInvalidValue;
+    }
+    p.F0 = g.F.p0;
+    p.F1 = g.f_planes ? g.F.p1 : nullptr;
+    p.ldF = g.F.ld;
+    p.bsF = g.F.bstride;
+    p.f_mode = g.f_planes ? 1 : 2;
+    p.dot_ws = g.dot_ws;
+  }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  auto planes_tma_ok = [&](const Mat& m) {
+    return m.ld % 8 == 0 && (g.batch == 1 || m.bstride % 8 == 0) && al16(m.p0) && (!m.p1 || al16(m.p1));
+  };
   if (g.Cp.p0) {
     p.Cp_hi = static_cast<__nv_bfloat16*>(g.Cp.p0);
     p.Cp_lo = static_cast<__nv_bfloat16*>(g.Cp.p1);
     p.ldCp = g.Cp.ld;
     p.bsCp = g.Cp.bstride;
-    if (g.Cp.ld % 8 == 0 && (g.batch == 1 || g.Cp.bstride % 8 == 0) && al16(g.Cp.p0) &&
-        (!g.Cp.p1 || al16(g.Cp.p1))) {
+    if (planes_tma_ok(g.Cp)) {
       if (!make_store_map(&p.tmC[0], g.Cp.p0, g.M, g.N, g.Cp.ld, g.Cp.bstride, g.batch, false))
         return cudaErrorInvalidValue;
       if (g.Cp.p1 && !make_store_map(&p.tmC[1], g.Cp.p1, g.M, g.N, g.Cp.ld, g.Cp.bstride, g.batch, false))
@@ -855,19 +1028,48 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
       p.tma_cp = 1;
     }
   }
+  if (g.Cp2.p0) {
+    if (g.Cp2.ld < g.N) {
+      set_error("gemm_tc: Cp2.ld < N");
+      return cudaErrorInvalidValue;
+    }
+    p.C2_hi = static_cast<__nv_bfloat16*>(g.Cp2.p0);
+    p.C2_lo = static_cast<__nv_bfloat16*>(g.Cp2.p1);
+    p.ldC2 = g.Cp2.ld;
+    p.bsC2 = g.Cp2.bstride;
+    p.c2_scale = g.c2_scale;
+    p.c2_eye = g.c2_eye;
+    if (planes_tma_ok(g.Cp2)) {
+      if (!make_store_map(&p.tmC2[0], g.Cp2.p0, g.M, g.N, g.Cp2.ld, g.Cp2.bstride, g.batch, false))
+        return cudaErrorInvalidValue;
+      if (g.Cp2.p1 && !make_store_map(&p.tmC2[1], g.Cp2.p1, g.M, g.N, g.Cp2.ld, g.Cp2.bstride, g.batch, false))
+        return cudaErrorInvalidValue;
+      p.tma_c2 = 1;
+    }
+  }
   if (g.Cf.p0) {
     p.Cf = static_cast<float*>(g.Cf.p0);
     p.ldCf = g.Cf.ld;
     p.bsCf = g.Cf.bstride;
     // one staging slot per chunk: fp32 takes the TMA path only when no plane output shares it
-    if (!g.Cp.p0 && g.Cf.ld % 4 == 0 && (p.batch == 1 || g.Cf.bstride % 4 == 0) && al16(g.Cf.p0)) {
+    if (!g.Cp.p0 && !g.Cp2.p0 && !g.X.p0 && g.Cf.ld % 4 == 0 && (p.batch == 1 || g.Cf.bstride % 4 == 0) &&
+        al16(g.Cf.p0)) {
       if (!make_store_map(&p.tmC[2], g.Cf.p0, g.M, g.N, g.Cf.ld, g.Cf.bstride, p.batch, true))
         return cudaErrorInvalidValue;
       p.tma_cf = 1;
     }
   }
-  if (ctas == 2) return npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
-  return npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
+  cudaError_t le;
+  if (ctas == 2) le = npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
+  else le = npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
+  if (le != cudaSuccess) return le;
+  if (g.dot_out) {
+    const int per_img = p.tiles_per_img * 4 * ctas;
+    dot_reduce_kernel<<<(g.batch + 7) / 8, 256, 0, stream>>>(g.dot_ws, per_img, g.batch, g.dot_out);
+    note_launch();
+    le = cudaGetLastError();
+  }
+  return le;
 }
 
 }  // namespace egm

@@ -509,6 +509,111 @@ __global__ void __launch_bounds__(256) triu_unpack_kernel(const float* __restric
   }
 }
 
+// packed upper triangle [B][L] (fp32 gradient of the half-vector) -> full D x D working matrix
+// out = s_b[b] * unpack(dv) with a zero lower triangle; optional per-block partial of
+// trace(unpack(dv)) (fixed order: tr_partial[b * gridDim.x + blockIdx.x]).
+constexpr int kUnpackRows = 8;
+__global__ void __launch_bounds__(256)
+triu_unpack_planes_kernel(const float* __restrict__ dv, long long ld_dv, int d,
+                          const float* __restrict__ s_b, WPtr out, float* __restrict__ tr_partial) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * kUnpackRows;
+  const float sc = s_b ? s_b[b] : 1.f;
+  const int groups = (int)(out.ld / 8);        // 8-column groups per row (ld % 8 == 0)
+  const float* src_b = dv + (long long)b * ld_dv;
+  float tr = 0.f;
+  for (int u = threadIdx.x; u < kUnpackRows * groups; u += blockDim.x) {
+    const int i = i0 + u / groups;
+    if (i >= d) break;
+    const int j0 = (u % groups) * 8;
+    const float* src = src_b + (long long)i * d - (long long)i * (i - 1) / 2 - i;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q;
+      const float x = (j >= i && j < d) ? src[j] : 0.f;
+      if (j == i) tr += x;
+      v[q] = sc * x;
+    }
+    const long long o = (long long)b * out.bs + (long long)i * out.ld + j0;
+    if (out.f) {
+      *reinterpret_cast<float4*>(out.f + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out.f + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+        hw[q] = __bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[q] = __bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(out.hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      if (out.lo) *reinterpret_cast<uint4*>(out.lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+  if (tr_partial) {
+    tr = block_sum(tr, sh);
+    if (threadIdx.x == 0) tr_partial[(long long)b * gridDim.x + blockIdx.x] = tr;
+  }
+}
+// fp32 matrix -> packed upper triangle as a working-matrix row (the Linear's operand)
+__global__ void __launch_bounds__(256)
+triu_pack_planes_kernel(const float* __restrict__ O, int d, WPtr out) {
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * kUnpackRows;
+  for (int r = 0; r < kUnpackRows; ++r) {
+    const int i = i0 + r;
+    if (i >= d) break;
+    const float* src = O + ((long long)b * d + i) * d;
+    const long long o = (long long)b * out.ld + (long long)i * d - (long long)i * (i - 1) / 2 - i;
+    for (int j = i + threadIdx.x; j < d; j += blockDim.x) wstore(out, o + j, src[j]);
+  }
+}
+// out[b] = sum_n dy[b,n] * (y[b,n] - bias[n])   ( = <dx_b, x_b> for y = x W^T + bias, dx = dy W )
+__global__ void rowdot_bias_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                   const float* __restrict__ bias, int batch, int n,
+                                   float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  for (int j = lane; j < n; j += 32)
+    a = fmaf(dy[(long long)b * n + j], y[(long long)b * n + j] - (bias ? bias[j] : 0.f), a);
+  a = warp_sum(a);
+  if (lane == 0) out[b] = a;
+}
+// tau -> tr, inv = 1/(tau+eps), post = (tau+eps)^-1/2        (scal rows 0,1,2 of [3,B])
+__global__ void mh_scalars_fwd_kernel(const float* __restrict__ tau, int batch, float eps,
+                                      float* __restrict__ scal) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float t = tau[b];
+  scal[b] = t;
+  scal[batch + b] = 1.f / (t + eps);
+  scal[2 * batch + b] = 1.f / sqrtf(t + eps);
+}
+// dM = inv dA + dtau I  with  dtau = (-1/2 <dO,O> - <dA,A>) inv
+__global__ void mh_dtau_kernel(const float* __restrict__ scal, int batch, const float* __restrict__ dotO,
+                               const float* __restrict__ dotA, float* __restrict__ dtau) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  dtau[b] = (-0.5f * dotO[b] - dotA[b]) * scal[batch + b];
+}
+// out[b] = sum of nper consecutive partials
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int nper, int batch,
+                                    float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= batch) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  for (int i = lane; i < nper; i += 32) a += partial[(long long)b * nper + i];
+  a = warp_sum(a);
+  if (lane == 0) out[b] = a;
+}
+
 // ----------------------------------------------------------------- sketch
 __global__ void sketch_fwd_kernel(const float* __restrict__ x, int batch, int d, int S,
                                   const int* __restrict__ off, const int* __restrict__ idx,
@@ -906,6 +1011,37 @@ void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* d
                  cudaStream_t st) {
   dim3 grid((n + 127) / 128, n, batch);
   pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, dG);
+  note_launch();
+}
+
+int triu_unpack_blocks(int d) { return (d + kUnpackRows - 1) / kUnpackRows; }
+void triu_unpack_planes(const float* dv, long long ld_dv, int batch, int d, const float* s_b,
+                        const W& out, float* tr_partial, int prec, cudaStream_t st) {
+  dim3 grid(triu_unpack_blocks(d), batch);
+  triu_unpack_planes_kernel<<<grid, 256, 0, st>>>(dv, ld_dv, d, s_b, wptr(out, prec), tr_partial);
+  note_launch();
+}
+void triu_pack_planes(const float* O, int batch, int d, const W& out, int prec, cudaStream_t st) {
+  dim3 grid((d + kUnpackRows - 1) / kUnpackRows, batch);
+  triu_pack_planes_kernel<<<grid, 256, 0, st>>>(O, d, wptr(out, prec));
+  note_launch();
+}
+void rowdot_bias(const float* dy, const float* y, const float* bias, int batch, int n, float* out,
+                 cudaStream_t st) {
+  rowdot_bias_kernel<<<(batch + 7) / 8, 256, 0, st>>>(dy, y, bias, batch, n, out);
+  note_launch();
+}
+void mh_scalars_fwd(const float* tau, int batch, float eps, float* scal, cudaStream_t st) {
+  mh_scalars_fwd_kernel<<<(batch + 127) / 128, 128, 0, st>>>(tau, batch, eps, scal);
+  note_launch();
+}
+void mh_dtau(const float* scal, int batch, const float* dotO, const float* dotA, float* dtau,
+             cudaStream_t st) {
+  mh_dtau_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scal, batch, dotO, dotA, dtau);
+  note_launch();
+}
+void sum_partials(const float* partial, int nper, int batch, float* out, cudaStream_t st) {
+  sum_partials_kernel<<<(batch + 7) / 8, 256, 0, st>>>(partial, nper, batch, out);
   note_launch();
 }
 

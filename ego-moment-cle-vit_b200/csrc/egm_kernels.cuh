@@ -122,6 +122,24 @@ void reduce_splits(const float* partial, int splits, int m, int n, const float* 
                    cudaStream_t st);
 void colsum(const float* x, int m, int n, float* out, cudaStream_t st);   // out[n] = sum_m x[m,n]
 
+// ---- fused moment head (pool -> iSQRT-COV -> packed half-vector as the Linear's operand)
+// out = s_b[b] * unpack(dv[b, :L]) as a D x D working matrix, zero lower triangle;
+// tr_partial (optional) [batch][triu_unpack_blocks(d)] partial traces of unpack(dv)
+int triu_unpack_blocks(int d);
+void triu_unpack_planes(const float* dv, long long ld_dv, int batch, int d, const float* s_b,
+                        const W& out, float* tr_partial, int prec, cudaStream_t st);
+// out (a [batch, d(d+1)/2] working matrix with batch == 1 image of `batch` rows) = triu(O)
+void triu_pack_planes(const float* O, int batch, int d, const W& out, int prec, cudaStream_t st);
+// out[b] = sum_n dy[b,n] (y[b,n] - bias[n])
+void rowdot_bias(const float* dy, const float* y, const float* bias, int batch, int n, float* out,
+                 cudaStream_t st);
+// scal rows: 0 tau, 1 inv = 1/(tau+eps), 2 post = (tau+eps)^-1/2
+void mh_scalars_fwd(const float* tau, int batch, float eps, float* scal, cudaStream_t st);
+// dtau = (-1/2 dotO - dotA) * inv
+void mh_dtau(const float* scal, int batch, const float* dotO, const float* dotA, float* dtau,
+             cudaStream_t st);
+void sum_partials(const float* partial, int nper, int batch, float* out, cudaStream_t st);
+
 // ---- pooling backward pieces
 // dmu = -(colsum(dZc) + sw*du/(t+eps))
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

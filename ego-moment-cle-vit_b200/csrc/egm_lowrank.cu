@@ -77,11 +77,13 @@ size_t egm_mlr_fwd_workspace(int B, int N, int D, int iters, int prec) {
 }
 
 int egm_mlr_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps, float* O,
-                float* u, float* vecs, float* mu, float* scal, void* state, int prec, void* ws,
-                size_t ws_bytes, egm_stream_t stream) {
+                void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_mlr_fwd: unknown precision mode %d", prec);
-  EGM_REQUIRE(Z && G && O && vecs && mu && scal && state, EGM_ERR_ARG, "egm_mlr_fwd: null pointer");
+  EGM_REQUIRE(Z && G && (O || x_planes) && vecs && mu && scal && state, EGM_ERR_ARG, "egm_mlr_fwd: null pointer");
+  EGM_REQUIRE(!x_planes || prec != PREC_FP32_SIMT, EGM_ERR_ARG,
+              "egm_mlr_fwd: the packed-planes output needs a tensor-core precision mode");
   EGM_REQUIRE(B > 0 && N > 0 && D > 0 && iters >= 1 && iters <= 64, EGM_ERR_ARG,
               "egm_mlr_fwd: bad sizes (needs iters >= 1)");
   const int K = iters;
@@ -124,7 +126,18 @@ int egm_mlr_fwd(const float* Z, const float* G, int B, int N, int D, int iters, 
   // X = Wn Q_K ; V = X Zc ; O = c1 Zc^T V + betaK I
   EGM_CUDA(Gb(N, N, B, prec).t(Wn, 0, S.Q(K), 0, N).outw(S.X()).run(st));
   EGM_CUDA(Gb(N, D, B, prec).t(S.X(), 0, Zc, 0, N).outw(S.V()).run(st));
-  EGM_CUDA(Gb(D, D, B, prec).t(Zc, 1, S.V(), 0, N).alpha(1.f, c1).eye(1.f, betaK).outf(O, D, D, D).run(st));
+  if (x_planes) {
+    // the result leaves as its packed upper triangle in operand planes (the Linear's x)
+    const long long L = (long long)D * (D + 1) / 2;
+    W X;
+    X.base = x_planes; X.rows = B; X.cols = (int)L; X.ld = w_ld((int)L); X.batch = 1;
+    Gb g(D, D, B, prec);
+    g.t(Zc, 1, S.V(), 0, N).alpha(1.f, c1).eye(1.f, betaK);
+    g.g.X = w_mat(X, prec);
+    EGM_CUDA(g.run(st));
+  } else {
+    EGM_CUDA(Gb(D, D, B, prec).t(Zc, 1, S.V(), 0, N).alpha(1.f, c1).eye(1.f, betaK).outf(O, D, D, D).run(st));
+  }
   return EGM_OK;
 }
 
@@ -133,17 +146,19 @@ size_t egm_mlr_bwd_workspace(int B, int N, int D, int iters, int prec) {
   const size_t nn = pad256(w_bytes(B, N, N)), nd = pad256(w_bytes(B, N, D));
   return pad256(w_bytes(B, D, D)) + nd + 14 * nn + 3 * pad256((size_t)B * N * D * 4) +
          pad256((size_t)B * N * egm_gpf_ldr(N) * 4) + pad256((size_t)B * D * 4) +
-         3 * pad256((size_t)B * N * 4) + 4 * pad256((size_t)B * 4) + 4096;
+         3 * pad256((size_t)B * N * 4) + 4 * pad256((size_t)B * 4) +
+         pad256((size_t)B * k::triu_unpack_blocks(D) * 4) + 4096;
 }
 
-int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G, const float* O,
-                const float* u, const float* vecs, const float* mu, const float* scal,
-                const void* state, int B, int N, int D, int iters, float eps, float* dZ, float* dG,
-                int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+int egm_mlr_bwd(const float* dO, const float* dv, const float* dotOO_in, const float* du, const float* Z,
+                const float* G, const float* O, const float* u, const float* vecs, const float* mu,
+                const float* scal, const void* state, int B, int N, int D, int iters, float eps,
+                float* dZ, float* dG, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_mlr_bwd: unknown precision mode %d", prec);
-  EGM_REQUIRE(dO && Z && G && O && vecs && mu && scal && state && dZ && dG, EGM_ERR_ARG,
-              "egm_mlr_bwd: null pointer");
+  EGM_REQUIRE(Z && G && vecs && mu && scal && state && dZ && dG, EGM_ERR_ARG, "egm_mlr_bwd: null pointer");
+  EGM_REQUIRE((dO && O) || (dv && dotOO_in), EGM_ERR_ARG,
+              "egm_mlr_bwd: needs either (dO, O) or the packed gradient (dv, <dO,O>)");
   EGM_REQUIRE(!du || u, EGM_ERR_ARG, "egm_mlr_bwd: du given without u");
   EGM_REQUIRE(B > 0 && N > 0 && D > 0 && iters >= 1 && iters <= 64, EGM_ERR_ARG, "egm_mlr_bwd: bad sizes");
   const int K = iters;
@@ -166,7 +181,8 @@ int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G
   float* dotOO = static_cast<float*>(ar.take((size_t)B * 4));
   float* dotHs = static_cast<float*>(ar.take((size_t)B * 4));
   float* dtaup = static_cast<float*>(ar.take((size_t)B * 4));
-  EGM_REQUIRE(dOw.base && dV.base && nn[13].base && P1 && P2 && dZc && dW && dmu && dw && ds && dt && trdO &&
+  float* trp = static_cast<float*>(ar.take((size_t)B * k::triu_unpack_blocks(D) * 4));
+  EGM_REQUIRE(trp && dOw.base && dV.base && nn[13].base && P1 && P2 && dZc && dW && dmu && dw && ds && dt && trdO &&
                   dotOO && dotHs && dtaup,
               EGM_ERR_WORKSPACE, "egm_mlr_bwd: workspace %zu < %zu", ws_bytes,
               egm_mlr_bwd_workspace(B, N, D, iters, prec));
@@ -177,9 +193,17 @@ int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G
   for (int k = 0; k < K; ++k) aK *= 1.5f;
   const long long dd = (long long)D * D;
 
-  k::batch_trace(dO, B, D, trdO, st);
-  k::batch_dot(dO, O, B, dd, dotOO, st);
-  k::affine(dO, D, dd, B, D, D, nullptr, 1.f, 0.f, dOw, 0.f, 0.f, nullptr, prec, st);
+  if (dv) {
+    // gradient of the packed half-vector: unpack straight into operand planes
+    const long long L = (long long)D * (D + 1) / 2;
+    k::triu_unpack_planes(dv, L, B, D, nullptr, dOw, trp, prec, st);
+    k::sum_partials(trp, k::triu_unpack_blocks(D), B, trdO, st);
+    dotOO = const_cast<float*>(dotOO_in);
+  } else {
+    k::batch_trace(dO, B, D, trdO, st);
+    k::batch_dot(dO, O, B, dd, dotOO, st);
+    k::affine(dO, D, dd, B, D, D, nullptr, 1.f, 0.f, dOw, 0.f, 0.f, nullptr, prec, st);
+  }
   EGM_LAUNCHED();
   // O = betaK I + c1 Zc^T V
   EGM_CUDA(Gb(N, D, B, prec).t(Zc, 0, dOw, 0, D).alpha(1.f, c1).outw(dV).run(st));             // dV = c1 Zc dO

@@ -206,9 +206,9 @@ class _MomentLowRankFunction(Function):
             state = _ws(L.egm_mlr_state_bytes(B, N, D, iters, prec), dev)
             ws = _ws(L.egm_mlr_fwd_workspace(B, N, D, iters, prec), dev)
             _lib.check(L.egm_mlr_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps),
-                                     O.data_ptr(), _p(u), vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(),
-                                     state.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
-                       "egm_mlr_fwd")
+                                     O.data_ptr(), None, _p(u), vecs.data_ptr(), mu.data_ptr(),
+                                     scal.data_ptr(), state.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                     _stream(dev)), "egm_mlr_fwd")
         ctx.save_for_backward(Z, G, O, vecs, mu, scal, state, *([u] if want_u else []))
         ctx.cfg = (int(iters), float(eps), bool(want_u), prec)
         if want_u:
@@ -234,11 +234,127 @@ class _MomentLowRankFunction(Function):
             dZ = torch.empty_like(Z)
             dG = torch.empty_like(G)
             ws = _ws(L.egm_mlr_bwd_workspace(B, N, D, iters, prec), dev)
-            _lib.check(L.egm_mlr_bwd(dO.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), O.data_ptr(), _p(u),
+            _lib.check(L.egm_mlr_bwd(dO.data_ptr(), None, None, _p(du), Z.data_ptr(), G.data_ptr(), O.data_ptr(), _p(u),
                                      vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
                                      B, N, D, iters, eps, dZ.data_ptr(), dG.data_ptr(), prec,
                                      ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mlr_bwd")
         return dZ, dG, None, None, None, None
+
+
+class _MomentHeadLinearFunction(Function):
+    """pool -> iSQRT-COV -> half-vectorise -> Linear, fused (csrc/egm_api.cu egm_mhd_*, or egm_mlr_*
+    for the low-rank evaluation): the packed upper triangle of the normalised covariance is
+    written by the last Newton-Schulz product straight into the Linear's operand planes."""
+
+    @staticmethod
+    def forward(ctx, Z, G, weight, bias, iters, eps, want_u, lowrank, prec):
+        L = _lib.load()
+        B, N, D = Z.shape
+        n_out, K = weight.shape
+        dev = Z.device
+        with torch.cuda.device(dev):
+            y = torch.empty(B, n_out, device=dev, dtype=torch.float32)
+            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
+            lin_state = _ws(L.egm_linear_state_bytes(B, n_out, K, prec), dev)
+            if lowrank:
+                scal = torch.empty(5, B, device=dev, dtype=torch.float32)
+                state = _ws(L.egm_mlr_state_bytes(B, N, D, iters, prec), dev)
+                ws = _ws(L.egm_mlr_fwd_workspace(B, N, D, iters, prec), dev)
+                _lib.check(L.egm_mlr_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps), None,
+                                         lin_state.data_ptr(), _p(u), vecs.data_ptr(), mu.data_ptr(),
+                                         scal.data_ptr(), state.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                         _stream(dev)), "egm_mlr_fwd")
+            else:
+                scal = torch.empty(3, B, device=dev, dtype=torch.float32)
+                state = _ws(L.egm_mhd_state_bytes(B, N, D, iters, prec), dev)
+                ws = _ws(L.egm_mhd_fwd_workspace(B, N, D, iters, prec), dev)
+                _lib.check(L.egm_mhd_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps),
+                                         lin_state.data_ptr(), _p(u), vecs.data_ptr(), mu.data_ptr(),
+                                         scal.data_ptr(), state.data_ptr(), prec, ws.data_ptr(), ws.numel(),
+                                         _stream(dev)), "egm_mhd_fwd")
+            ws = _ws(L.egm_linear_fwd_workspace(B, n_out, K, prec), dev)
+            _lib.check(L.egm_linear_fwd(None, weight.data_ptr(), _p(bias), B, n_out, K, y.data_ptr(),
+                                        lin_state.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_linear_fwd")
+        ctx.save_for_backward(Z, G, vecs, mu, scal, state, lin_state, y, *([bias] if bias is not None else []),
+                              *([u] if want_u else []))
+        ctx.cfg = (int(iters), float(eps), bool(want_u), bool(lowrank), prec, bias is not None, n_out, K)
+        if want_u:
+            return y, u
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, du=None):
+        L = _lib.load()
+        iters, eps, want_u, lowrank, prec, has_bias, n_out, K = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        Z, G, vecs, mu, scal, state, lin_state, y = saved[:8]
+        rest = saved[8:]
+        bias = rest.pop(0) if has_bias else None
+        u = rest.pop(0) if want_u else None
+        B, N, D = Z.shape
+        dev = Z.device
+        need_w = ctx.needs_input_grad[2]
+        need_b = has_bias and ctx.needs_input_grad[3]
+        with torch.cuda.device(dev):
+            if dy is None:
+                dy = torch.zeros(B, n_out, device=dev, dtype=torch.float32)
+            dy = dy.contiguous()
+            if du is not None:
+                du = du.contiguous()
+            dv = torch.empty(B, K, device=dev, dtype=torch.float32)
+            dw = torch.empty(n_out, K, device=dev, dtype=torch.float32) if need_w else None
+            db = torch.empty(n_out, device=dev, dtype=torch.float32) if need_b else None
+            ws = _ws(L.egm_linear_bwd_workspace(B, n_out, K, prec), dev)
+            _lib.check(L.egm_linear_bwd(dy.data_ptr(), lin_state.data_ptr(), B, n_out, K, dv.data_ptr(),
+                                        _p(dw), _p(db), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
+                       "egm_linear_bwd")
+            dot = torch.empty(B, device=dev, dtype=torch.float32)   # <dO, O> = <dy, y - bias>
+            _lib.check(L.egm_rowdot_bias(dy.data_ptr(), y.data_ptr(), _p(bias), B, n_out, dot.data_ptr(),
+                                         _stream(dev)), "egm_rowdot_bias")
+            dZ = torch.empty_like(Z)
+            dG = torch.empty_like(G)
+            if lowrank:
+                ws = _ws(L.egm_mlr_bwd_workspace(B, N, D, iters, prec), dev)
+                _lib.check(L.egm_mlr_bwd(None, dv.data_ptr(), dot.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(),
+                                         None, _p(u), vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(),
+                                         state.data_ptr(), B, N, D, iters, eps, dZ.data_ptr(), dG.data_ptr(),
+                                         prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mlr_bwd")
+            else:
+                ws = _ws(L.egm_mhd_bwd_workspace(B, N, D, iters, prec), dev)
+                _lib.check(L.egm_mhd_bwd(dv.data_ptr(), dot.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), _p(u),
+                                         vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
+                                         B, N, D, iters, eps, dZ.data_ptr(), dG.data_ptr(), prec,
+                                         ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mhd_bwd")
+        return dZ, dG, dw, db, None, None, None, None, None
+
+
+def moment_head_linear(tokens, graph, weight, bias, num_iterations, *, eps=1e-5, third_order=False,
+                       precision=None, algorithm=None):
+    """Linear(half_vectorize(NewtonSchulzSqrtm(Zc^T W Zc)))  (moment_head.py:279-300, first layer of
+    second_net) as one fused operator; returns y [B, n_out] or (y, u). Returns None when the fused
+    form does not apply (strict fp32 mode, or fewer iterations than the fused chain supports) - the
+    caller then composes graph_weighted_pool / newton_schulz / half_vectorize / linear."""
+    prec = _prec(precision)
+    algo = algorithm or _ns_algorithm
+    if prec == _lib.PREC_FP32_SIMT:
+        return None
+    Z = _require_cuda_f32("tokens", tokens, 3)
+    G = _require_cuda_f32("graph", graph, 3)
+    if G.shape != (Z.shape[0], Z.shape[1], Z.shape[1]):
+        raise RuntimeError(f"graph shape {tuple(G.shape)} does not match tokens {tuple(Z.shape)}")
+    lowrank = algo == "lowrank" and num_iterations >= 1 and Z.shape[1] < Z.shape[2]
+    if not lowrank and num_iterations < 2:
+        return None
+    w = _require_cuda_f32("weight", weight, 2)
+    D = Z.shape[2]
+    if w.shape[1] != D * (D + 1) // 2:
+        raise RuntimeError(f"linear: weight {tuple(w.shape)} does not match d_in={D}")
+    b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
+    return _MomentHeadLinearFunction.apply(Z, G, w, b, int(num_iterations), eps, third_order, lowrank, prec)
 
 
 _ns_algorithm = os.environ.get("EGM_NS_ALGORITHM", "dense")

@@ -125,6 +125,19 @@ class MomentHead(nn.Module):
         return torch.einsum('bn,bnd->bd', w, tokens) / (tr + self.eps)
 
     def forward(self, tokens: torch.Tensor, graph: torch.Tensor) -> torch.Tensor:
+        # fused operator: pool -> iSQRT-COV -> half-vector -> Linear of second_net, no fp32 round
+        # trips between the stages (tensor-core precision modes)
+        lin = self.second_net[0]
+        fused = EF.moment_head_linear(tokens, graph, lin.weight, lin.bias, self.isqrt_cov.num_iterations,
+                                      eps=self.eps, third_order=self.use_third_order)
+        if fused is not None:
+            y, u = fused if self.use_third_order else (fused, None)
+            for layer in list(self.second_net)[1:]:
+                y = layer(y)
+            features = [y]
+            if self.use_third_order:
+                features.append(self._feature_net(self.third_net, self.tensor_sketch(u)))
+            return torch.cat(features, dim=-1)
         if EF.get_ns_algorithm() == "lowrank":
             # opt-in: same function, Newton-Schulz on N x N matrices (functional.moment_isqrt)
             res = EF.moment_isqrt(tokens, graph, self.isqrt_cov.num_iterations, eps=self.eps,

@@ -21,6 +21,9 @@
  *   egm_ns_fwd/bwd       NewtonSchulzSqrtm.forward              src/models/moment_head.py:28-70
  *                        matrix_sqrt_newton_schulz (post_mode 1) src/utils/ops.py:122-165
  *   egm_mlr_fwd/bwd      the same pooling + iSQRT-COV lines, low-rank evaluation (opt-in)
+ *   egm_mhd_fwd/bwd      MomentHead.forward 2nd-order branch    src/models/moment_head.py:279-300
+ *                        (pool -> NewtonSchulzSqrtm -> _half_vectorize fused, dense D x D chain)
+ *   egm_linear_fwd/bwd   nn.Linear of second_net / third_net    src/models/moment_head.py:186-200
  *   egm_triu_pack/unpack MomentHead._half_vectorize             src/models/moment_head.py:202-220
  *                        half_vectorize_symmetric               src/utils/ops.py:100-119
  *   egm_sketch_fwd/bwd   TensorSketch.forward/_count_sketch     src/models/moment_head.py:100-133
@@ -102,18 +105,45 @@ int egm_ns_bwd(const float* dO, const float* O, const float* M, const float* sca
  * moment_head.py:279-296. iters >= 1. Saved: vecs, mu (as egm_pool_fwd), scal [5,B], state. */
 size_t egm_mlr_state_bytes(int B, int N, int D, int iters, int prec);
 size_t egm_mlr_fwd_workspace(int B, int N, int D, int iters, int prec);
+/* Output: O [B,D,D] fp32, or (x_planes != NULL, tensor-core modes) the packed upper triangle of O
+ * written as operand planes straight into the `state` of egm_linear_fwd (see egm_mhd_fwd).
+ * Backward takes either (dO, O) or the packed gradient dv [B, D(D+1)/2] with dotOO = <dO,O> [B]. */
 int egm_mlr_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps, float* O,
-                float* u, float* vecs, float* mu, float* scal, void* state, int prec, void* ws,
-                size_t ws_bytes, egm_stream_t stream);
+                void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream);
 size_t egm_mlr_bwd_workspace(int B, int N, int D, int iters, int prec);
-int egm_mlr_bwd(const float* dO, const float* du, const float* Z, const float* G, const float* O,
-                const float* u, const float* vecs, const float* mu, const float* scal,
-                const void* state, int B, int N, int D, int iters, float eps, float* dZ, float* dG,
-                int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+int egm_mlr_bwd(const float* dO, const float* dv, const float* dotOO, const float* du, const float* Z,
+                const float* G, const float* O, const float* u, const float* vecs, const float* mu,
+                const float* scal, const void* state, int B, int N, int D, int iters, float eps,
+                float* dZ, float* dG, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+
+/* ---- fused dense moment head: pooling -> iSQRT-COV -> packed half-vector -----------------------
+ * MomentHead.forward up to the input of second_net's Linear (moment_head.py:279-300), D x D
+ * Newton-Schulz chain, every intermediate kept in the GEMM engine's operand format (no fp32
+ * M2 / O / dO / dM round trips; trace(M2) and <dA,A> are by-products of GEMM epilogues).
+ * x_planes: the operand region of egm_linear_fwd's `state` for (M=B, K=D(D+1)/2): the packed upper
+ * triangle of iSQRT-COV(M2) is written there, then egm_linear_fwd is called with x == NULL.
+ * Backward: dv [B, D(D+1)/2] = gradient of the half-vector (egm_linear_bwd's dx), dotO [B] =
+ * <dv_b, v_b> (for y = v W^T + b this equals <dy_b, y_b - b>: egm_rowdot_bias).
+ * iters >= 2, tensor-core precision modes only. Saved: vecs, mu (as egm_pool_fwd), scal [3,B], state. */
+size_t egm_mhd_state_bytes(int B, int N, int D, int iters, int prec);
+size_t egm_mhd_fwd_workspace(int B, int N, int D, int iters, int prec);
+int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps,
+                void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream);
+size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec);
+int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float* Z, const float* G,
+                const float* u, const float* vecs, const float* mu, const float* scal, const void* state,
+                int B, int N, int D, int iters, float eps, float* dZ, float* dG, int prec, void* ws,
+                size_t ws_bytes, egm_stream_t stream);
+/* out[b] = sum_n dy[b,n] * (y[b,n] - bias[n])   (bias may be NULL) */
+int egm_rowdot_bias(const float* dy, const float* y, const float* bias, int B, int n, float* out,
+                    egm_stream_t stream);
 
 /* ---- Linear layers of second_net / third_net (nn.Linear at moment_head.py:187,196) -------------
  * y [M,N] = x [M,K] W^T [N,K] + bias [N] on the tcgen05 engine with split-K; state keeps the
  * operand planes for the backward (dx = dy W, dW = dy^T x, dbias = colsum dy; any may be null).
+ * x == NULL: the x operand planes were already written into `state` by egm_mhd_fwd / egm_mlr_fwd.
  * Tensor-core precision modes only (the strict fp32 mode leaves this GEMM to the caller). */
 size_t egm_linear_state_bytes(int M, int N, int K, int prec);
 size_t egm_linear_fwd_workspace(int M, int N, int K, int prec);

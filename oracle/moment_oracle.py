@@ -295,8 +295,9 @@ def moment_forward(tokens, graph, iters, eps=1e-5, third=None, dtype=np.float64,
 
 
 def moment_backward(tokens, graph, iters, dvec, eps=1e-5, third=None, dsketch=None, dtype=np.float64,
-                    fwd=None):
-    """Reverse mode of moment_forward: returns (d tokens, d graph) given d vec (and d sketch).
+                    fwd=None, du=None):
+    """Reverse mode of moment_forward: returns (d tokens, d graph) given d vec (and d sketch, or
+    directly the gradient `du` of the third-order weighted mean u, moment_head.py:305-311).
     `fwd` = moment_forward(..., keep=True) output, to reuse saved tensors as autograd would."""
     Z = np.asarray(tokens, dtype)
     G = np.asarray(graph, dtype)
@@ -317,10 +318,12 @@ def moment_backward(tokens, graph, iters, dvec, eps=1e-5, third=None, dsketch=No
     dW = _mm(_mm(Zc, dM), _bT(Zc))
     dw = np.zeros((B, N), dtype)
     dt = np.zeros((B,), dtype)
-    if third is not None and dsketch is not None:
+    if (third is not None and dsketch is not None) or du is not None:
         u = np.einsum("bnd,bn->bd", Zc, w) / te
-        du = tensor_sketch_backward(u, third["hashes"], third["signs"], third["sketch_dim"],
-                                    np.asarray(dsketch, dtype))
+        if du is None:
+            du = tensor_sketch_backward(u, third["hashes"], third["signs"], third["sketch_dim"],
+                                        np.asarray(dsketch, dtype))
+        du = np.asarray(du, dtype)
         dZc = dZc + w[:, :, None] * du[:, None, :] / te[:, :, None]
         dw = dw + np.einsum("bnd,bd->bn", Zc, du) / te
         dt = dt - np.sum(u * du, axis=-1) / te[:, 0]

@@ -93,6 +93,9 @@ struct Case {
   int pad;         // extra leading-dimension padding (elements, multiple of 8)
   int f32_unaligned;  // fp32 output with ld == N (exercises the scalar store path)
   int sample;      // verify only `sample` random entries per image (0 = all)
+  int c2;          // also request the secondary plane output  -0.5*C + 1.5*I
+  int dot;         // also request <C, F> per image (F: planes)
+  int triu;        // output = packed upper triangle planes (excludes out_planes)
 };
 
 static int run_case(const Case& c) {
@@ -137,6 +140,31 @@ static int run_case(const Case& c) {
     CK(cudaMemset(d_cf, 0xFF, bsf * c.batch * 4));
     g.Cf.p0 = d_cf; g.Cf.rows = c.M; g.Cf.cols = c.N; g.Cf.ld = ldf; g.Cf.bstride = bsf;
   }
+  __nv_bfloat16 *d_c2h = nullptr, *d_c2l = nullptr;
+  if (c.c2) {
+    CK(cudaMalloc(&d_c2h, bsp * c.batch * 2)); CK(cudaMalloc(&d_c2l, bsp * c.batch * 2));
+    CK(cudaMemset(d_c2h, 0xFF, bsp * c.batch * 2)); CK(cudaMemset(d_c2l, 0xFF, bsp * c.batch * 2));
+    g.Cp2.p0 = d_c2h; g.Cp2.p1 = (c.npass == 3) ? d_c2l : nullptr; g.Cp2.rows = c.M; g.Cp2.cols = c.N;
+    g.Cp2.ld = ldp; g.Cp2.bstride = bsp; g.c2_scale = -0.5f; g.c2_eye = 1.5f;
+  }
+  HostMat F;
+  float *d_dot = nullptr, *d_dotws = nullptr;
+  if (c.dot) {
+    F.init(c.M, c.N, c.batch, c.pad, true);
+    g.F = F.planes(); g.f_planes = 1;
+    if (c.npass != 3) g.F.p1 = nullptr;
+    CK(cudaMalloc(&d_dot, c.batch * 4));
+    g.dot_out = d_dot;
+    CK(cudaMalloc(&d_dotws, egm::gemm_tc_dot_ws_floats(g) * 4 + 16));
+    g.dot_ws = d_dotws;
+  }
+  const long long Lx = (long long)c.N * (c.N + 1) / 2, ldx = (Lx + 7) / 8 * 8;
+  __nv_bfloat16 *d_xh = nullptr, *d_xl = nullptr;
+  if (c.triu) {
+    CK(cudaMalloc(&d_xh, ldx * c.batch * 2)); CK(cudaMalloc(&d_xl, ldx * c.batch * 2));
+    CK(cudaMemset(d_xh, 0xFF, ldx * c.batch * 2)); CK(cudaMemset(d_xl, 0xFF, ldx * c.batch * 2));
+    g.X.p0 = d_xh; g.X.p1 = (c.npass == 3) ? d_xl : nullptr; g.X.ld = ldx;
+  }
   cudaError_t le = egm::gemm_tc(g, c.npass, 0);
   if (le != cudaSuccess) {
     printf("[FAIL] %-44s launch: %s (%s)\n", c.name, cudaGetErrorString(le), egm::last_error());
@@ -155,6 +183,21 @@ static int run_case(const Case& c) {
   }
   if (c.out_f32) { cf.resize(bsf * c.batch); CK(cudaMemcpy(cf.data(), d_cf, cf.size() * 4, cudaMemcpyDeviceToHost)); }
 
+  std::vector<__nv_bfloat16> c2h, c2l, xh, xl;
+  std::vector<float> dots;
+  if (c.c2) {
+    c2h.resize(bsp * c.batch); c2l.resize(bsp * c.batch);
+    CK(cudaMemcpy(c2h.data(), d_c2h, c2h.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c2l.data(), d_c2l, c2l.size() * 2, cudaMemcpyDeviceToHost));
+  }
+  if (c.triu) {
+    xh.resize(ldx * c.batch); xl.resize(ldx * c.batch);
+    CK(cudaMemcpy(xh.data(), d_xh, xh.size() * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(xl.data(), d_xl, xl.size() * 2, cudaMemcpyDeviceToHost));
+  }
+  if (c.dot) { dots.resize(c.batch); CK(cudaMemcpy(dots.data(), d_dot, c.batch * 4, cudaMemcpyDeviceToHost)); }
+  double max_err_c2 = 0, max_err_x = 0, max_err_dot = 0;
+  std::vector<double> dot_ref(c.batch, 0.0), dot_abs(c.batch, 0.0);
   double max_ref = 0, max_err_f = 0, max_err_p = 0;
   int wb = 0, wm = 0, wn = 0; double wgot = 0, wref = 0;
   uint32_t s = 777;
@@ -176,6 +219,24 @@ static int run_case(const Case& c) {
       if (c.e_mode == 1) ref += c.gamma * E.val(b, m, n, c.npass == 3 ? 3 : 1);
       if (c.e_mode == 2) ref += c.gamma * (double)E.f[(size_t)b * E.bs + (size_t)m * E.ld + n];
       if (fabs(ref) > max_ref) max_ref = fabs(ref);
+      if (c.c2) {
+        size_t o = (size_t)b * bsp + (size_t)m * ldp + n;
+        double got = __bfloat162float(c2h[o]);
+        if (c.npass == 3) got += __bfloat162float(c2l[o]);
+        double e = fabs(got - (-0.5 * ref + (m == n ? 1.5 : 0.0)));
+        if (e > max_err_c2) max_err_c2 = e;
+      }
+      if (c.dot) {
+        double f = F.val(b, m, n, c.npass == 3 ? 3 : 1);
+        dot_ref[b] += ref * f; dot_abs[b] += fabs(ref * f);
+      }
+      if (c.triu && n >= m) {
+        size_t o = (size_t)b * ldx + (size_t)m * c.N - (size_t)m * (m - 1) / 2 + (n - m);
+        double got = __bfloat162float(xh[o]);
+        if (c.npass == 3) got += __bfloat162float(xl[o]);
+        double e = fabs(got - ref);
+        if (!(e <= max_err_x)) { max_err_x = e; wb = b; wm = m; wn = n; wgot = got; wref = ref; }
+      }
       if (c.out_f32) {
         double got = cf[(size_t)b * bsf + (size_t)m * ldf + n];
         double e = fabs(got - ref);
@@ -193,14 +254,33 @@ static int run_case(const Case& c) {
   const double tol_f = (c.npass == 3) ? 5e-5 : 2e-5;
   const double tol_p = (c.npass == 3) ? 8e-5 : 6e-3;  // single plane output: bf16 rounding
   const double rf = max_err_f / (max_ref + 1e-30), rp = max_err_p / (max_ref + 1e-30);
-  const bool ok = (!c.out_f32 || rf < tol_f) && (!c.out_planes || rp < tol_p) && max_ref > 0;
+  if (c.dot)
+    for (int b = 0; b < c.batch; ++b) {
+      double e = fabs(dots[b] - dot_ref[b]) / (dot_abs[b] + 1e-30);
+      if (!(e <= max_err_dot)) max_err_dot = e;
+    }
+  const double rc2 = max_err_c2 / (max_ref + 1e-30), rx = max_err_x / (max_ref + 1e-30);
+  // padding of the packed rows must stay untouched (0xFFFF) and nothing may be written twice wrong
+  bool pad_ok = true;
+  if (c.triu)
+    for (int b = 0; b < c.batch && pad_ok; ++b)
+      for (long long j = Lx; j < ldx; ++j)
+        if (__bfloat16_as_ushort(xh[(size_t)b * ldx + j]) != 0xFFFF) pad_ok = false;
+  const bool ok = (!c.out_f32 || rf < tol_f) && (!c.out_planes || rp < tol_p) && max_ref > 0 &&
+                  (!c.c2 || rc2 < tol_p) && (!c.triu || (rx < tol_p && pad_ok)) &&
+                  (!c.dot || max_err_dot < (c.sample ? 1e30 : 2e-5));
   printf("[%s] %-44s rel_err f32=%.2e planes=%.2e (max|ref|=%.3g)", ok ? " ok " : "FAIL", c.name, rf, rp, max_ref);
+  if (c.c2) printf(" c2=%.2e", rc2);
+  if (c.triu) printf(" triu=%.2e%s", rx, pad_ok ? "" : " PAD-CLOBBERED");
+  if (c.dot) printf(" dot=%.2e", max_err_dot);
   if (!ok) printf("  worst b=%d m=%d n=%d got=%.6g ref=%.6g", wb, wm, wn, wgot, wref);
   printf("\n");
   fflush(stdout);
   for (int t = 0; t < c.nterms; ++t) { A[t].free_(); B[t].free_(); }
   if (c.e_mode) E.free_();
   cudaFree(d_ch); cudaFree(d_cl); cudaFree(d_cf); cudaFree(d_alpha_b);
+  cudaFree(d_c2h); cudaFree(d_c2l); cudaFree(d_xh); cudaFree(d_xl); cudaFree(d_dot); cudaFree(d_dotws);
+  if (c.dot) F.free_();
   return ok ? 0 : 1;
 }
 
@@ -265,6 +345,14 @@ int main(int argc, char** argv) {
       {"two-term dY T^T + Z^T dP 384 b2 x3",    384, 384, 2, 2, {384, 384}, {0, 1}, {1, 0}, 3, 1.f, 0.f, 0.f, 0, 0, 1, 1, 0, 0, 4000},
       {"two-term + planes addend + alpha_b",    200, 264, 3, 2, {72, 136}, {1, 0}, {0, 1}, 3, 0.75f, 0.f, -0.5f, 1, 1, 1, 1, 8, 0, 0},
       {"f32 addend, x1, small 64x64x64",        64, 64, 2, 1, {64, 0},   {0, 0}, {0, 0}, 1, 2.f, 3.f, 1.f, 2, 0, 1, 1, 0, 0, 0},
+      // secondary plane output + <C,F> + alpha_b (A = M/tau and T_0 from one product)
+      {"Cp2 + dot, 300x300x197 b3 x3 alpha_b",  300, 300, 3, 1, {197, 0}, {1, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0},
+      {"Cp2 + dot, 200x264 b2 x1 ragged, f32",  200, 264, 2, 1, {72, 0},  {0, 0}, {1, 0}, 1, 0.5f, 0.25f, -0.5f, 1, 0, 1, 1, 8, 0, 0, 1, 1, 0},
+      {"dot only U=W Zc 197x768x197 b2 x3",     197, 768, 2, 1, {197, 0}, {0, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0},
+      // packed upper triangle (+ fp32 copy of the full matrix is excluded where tiles are skipped)
+      {"triu packed 768^3 b2 x3 post-scaled",   768, 768, 2, 1, {768, 0}, {0, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1},
+      {"triu packed 300x300x96 b3 x1 ragged",   300, 300, 3, 1, {96, 0},  {0, 0}, {1, 0}, 1, -0.5f, 1.5f, 0.f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1},
+      {"triu packed 197x197x64 b2 x3 1 tile",   197, 197, 2, 1, {64, 0},  {1, 0}, {0, 0}, 3, 1.f, 0.f, 0.5f, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1},
   };
   const int ncases = sizeof(cases) / sizeof(cases[0]);
   for (int i = 0; i < ncases; ++i) fails += run_case(cases[i]);

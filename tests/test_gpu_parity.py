@@ -153,6 +153,55 @@ def test_moment_head_lowrank_switch(pkg, dev):
         EF.set_ns_algorithm("magic")
 
 
+@pytest.mark.parametrize("algo,K", [("dense", 2), ("dense", 3), ("dense", 5), ("lowrank", 1), ("lowrank", 4)])
+@pytest.mark.parametrize("shape", [(3, 21, 40), (2, 50, 136), (2, 70, 64)])
+def test_fused_moment_head_linear_matches_the_oracle(pkg, dev, algo, K, shape):
+    """functional.moment_head_linear: pool -> iSQRT-COV -> packed half-vector -> Linear in one
+    operator (the last Newton-Schulz product writes the Linear's operand planes; trace(M2), <dO,O>
+    and <dA,A> come out of GEMM epilogues). Same outputs and gradients as the oracle's restatement
+    of moment_head.py:279-300 followed by a Linear, incl. the third-order u branch and a
+    non-symmetric graph."""
+    EF = pkg.functional
+    B, N, D = shape
+    g = torch.Generator().manual_seed(7 * K + N)
+    Z = torch.randn(B, N, D, generator=g)
+    graph = torch.rand(B, N, N, generator=g) + 0.05        # not symmetric
+    L, n_out = D * (D + 1) // 2, 24
+    Wt = torch.randn(n_out, L, generator=g) / L ** 0.5
+    bias = torch.randn(n_out, generator=g)
+    dy = torch.randn(B, n_out, generator=g)
+    du = torch.randn(B, D, generator=g)
+    st = O.moment_forward(npy(Z), npy(graph), K, 1e-5, {"hashes": np.zeros((3, D), np.int64),
+                                                        "signs": np.ones((3, D), np.int64), "sketch_dim": 4})
+    y_ref = st["vec"] @ npy(Wt).T + npy(bias)
+    dvec = npy(dy) @ npy(Wt)
+    for mode, tol in (("fp32", 1e-3), ("bf16", 6e-2)):
+        with EF.precision(mode):
+            z = Z.to(dev).requires_grad_(True)
+            gr = graph.to(dev).requires_grad_(True)
+            w = Wt.to(dev).requires_grad_(True)
+            b = bias.to(dev).requires_grad_(True)
+            res = EF.moment_head_linear(z, gr, w, b, K, eps=1e-5, third_order=True, algorithm=algo)
+            if algo == "lowrank" and N >= D:
+                # N >= D: the low-rank form does not apply, the dense fused chain needs K >= 2
+                assert (res is None) == (K < 2)
+                if res is None:
+                    continue
+            y, u = res
+            ((y * dy.to(dev)).sum() + (u * du.to(dev)).sum()).backward()
+        assert rel_err(npy(y), y_ref) < tol
+        assert rel_err(npy(u), st["u"]) < tol
+        # gradients: the oracle's backward takes d vec and (through the sketch hook) d u
+        dZ, dG = O.moment_backward(npy(Z), npy(graph), K, dvec, 1e-5, None, None, du=npy(du))
+        assert rel_err(npy(z.grad), dZ) < 3 * tol
+        assert rel_err(npy(gr.grad), dG) < 3 * tol
+        assert rel_err(npy(w.grad), npy(dy).T @ st["vec"]) < tol
+        assert rel_err(npy(b.grad), npy(dy).sum(0)) < 1e-5
+    # strict fp32 mode and K < 2 fall back to the composed operators
+    with EF.precision("fp32_simt"):
+        assert EF.moment_head_linear(Z.to(dev), graph.to(dev), Wt.to(dev), None, K) is None
+
+
 # ----------------------------------------------------------- golden fixtures (reference)
 def _build_from_golden(pkg, rec, dev):
     B, N, D, P, Q, K, d_out, third, S, sym, train = [int(v) for v in rec["cfg"]]
