@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--algorithm", default="dense", choices=["dense", "lowrank"],
                     help="iSQRT-COV evaluation: D x D Newton-Schulz chain, or the N x N low-rank form")
     ap.add_argument("--no-extras", action="store_true", help="skip bf16-mode / cpu-baseline side runs")
+    ap.add_argument("--gemm-breakdown", action="store_true",
+                    help="print the per-shape time of the GEMM-engine launches to stderr")
     return ap.parse_args()
 
 
@@ -229,20 +231,16 @@ def run_native(args):
     d_out = torch.randn(B, D_OUT, device=dev, generator=gen)
     h2d_bytes = 2 * B * N_TOK * D_IN * 4
 
-    # live timing of the Newton-Schulz chain (the tcgen05 GEMM engine) inside the timed steps
-    ns_events = []
-    orig_ns = EF.newton_schulz
-
-    def timed_ns(matrix, num_iterations, eps=1e-5, *, post="divide", precision=None):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        out = orig_ns(matrix, num_iterations, eps, post=post, precision=precision)
-        ev[1].record()
-        if matrix.requires_grad:
-            matrix.register_hook(lambda g, e=ev[3]: e.record())      # after the NS backward
-            out.register_hook(lambda g, e=ev[2]: e.record())         # before the NS backward
-            ns_events.append(ev)
-        return out
+    # live timing of the tcgen05 GEMM engine inside the timed steps: the library brackets every
+    # engine launch with two CUDA events on the launching stream (egm_prof_*, include/egm_b200.h)
+    def read_prof():
+        import ctypes
+        recs = []
+        ms, fl, dims = ctypes.c_float(), ctypes.c_double(), (ctypes.c_int * 6)()
+        for i in range(lib.egm_prof_count()):
+            if lib.egm_prof_read(i, ctypes.byref(ms), ctypes.byref(fl), dims) == 0:
+                recs.append((ms.value, fl.value, tuple(dims)))
+        return recs
 
     def step(a, p):
         a = a.requires_grad_(True)
@@ -319,20 +317,34 @@ def run_native(args):
             loss_ready[slot].synchronize()
             e2e_losses.append(float(loss_host[slot]))
 
-    mods = sys.modules["ego-moment-cle-vit_b200.models.moment_head"]
     for i in range(max(args.warmup, 3)):
         resident_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region: device-resident inputs, NS chain bracketed by events
-    mods.EF.newton_schulz = timed_ns
+    # ---- timed region: device-resident inputs, every GEMM-engine launch bracketed by events
+    lib.egm_prof_reset()
+    lib.egm_prof_enable(1)
     l0 = lib.egm_launch_count()
     ms_total = timed(resident_step, args.steps)
     launches = (lib.egm_launch_count() - l0) / args.steps
-    mods.EF.newton_schulz = orig_ns
-    ns_f = sum(e[0].elapsed_time(e[1]) for e in ns_events) / max(1, len(ns_events))
-    ns_b = sum(e[2].elapsed_time(e[3]) for e in ns_events) / max(1, len(ns_events))
+    lib.egm_prof_enable(0)
+    prof = read_prof()
+    lib.egm_prof_reset()
+    # the Newton-Schulz chain = the D x D x D products (dense algorithm)
+    ns = [r for r in prof if r[2][0] == D_IN and r[2][1] == D_IN and r[2][2] == D_IN]
+    ns_ms = sum(r[0] for r in ns) / args.steps
+    ns_flops = sum(r[1] for r in ns) / args.steps
+    gemm_ms = sum(r[0] for r in prof) / args.steps
+    gemm_flops = sum(r[1] for r in prof) / args.steps
+    if args.gemm_breakdown and rank == 0:
+        by = {}
+        for ms_i, fl_i, d in prof:
+            e = by.setdefault(d, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += ms_i; e[2] += fl_i
+        for d, (n, ms_i, fl_i) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+            print(f"gemm M={d[0]} N={d[1]} K={d[2]}+{d[3]} batch={d[4]} x{d[5]}: {n / args.steps:.1f}/step "
+                  f"{ms_i / args.steps:.3f} ms/step {fl_i / ms_i / 1e9:.0f} TFLOP/s algorithmic", file=sys.stderr)
     # ---- end to end: host buffers, copies inside the timed region
     for ev in consumed:
         ev.record()
@@ -387,17 +399,29 @@ def run_native(args):
     if not peak_tf:
         peak_tf, peak_src = 1400.0, "B200_PROFILING.md sustained fallback (of fallback)"
     passes = 3 if args.precision == "fp32" else 1
-    n_gemm = (3 * NS_ITERS - 3) + (6 * NS_ITERS - 6)          # products actually evaluated: 12 + 24
-    ns_flops = n_gemm * 2.0 * D_IN ** 3 * B
-    ns_ms = ns_f + ns_b
-    achieved = ns_flops / (ns_ms * 1e-3) / 1e12 if ns_ms > 0 else None
+    dense = args.algorithm == "dense" and ns_ms > 0
+    k_ms, k_flops, k_n = (ns_ms, ns_flops, len(ns) / args.steps) if dense else (gemm_ms, gemm_flops, len(prof) / args.steps)
+    achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("gemm_tc2_kernel_dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (Newton-Schulz chain fwd+bwd, per GPU)",
+        "bound": "tensor",
+        "kernel": "gemm_tc2_kernel<%d> (%s, per GPU)" % (passes, "Newton-Schulz chain fwd+bwd: the D x D x D products"
+                                                        if dense else "all tcgen05 GEMM launches of the step"),
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+        "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
         "peak_source": peak_src,
-        "algorithmic_flops_per_step": ns_flops, "gemms_per_step": n_gemm,
-        "ns_chain_ms": {"fwd": ns_f, "bwd": ns_b}, "share_of_step": ns_ms / ms_step,
+        "how": "per-launch CUDA events on the launching stream inside the timed steps (egm_prof_*)",
+        "launches_per_step": k_n, "kernel_ms_per_step": k_ms,
+        "avg_launch_ms": (k_ms / k_n) if k_n else None,
+        "algorithmic_flops_per_step": k_flops,
+        "share_of_step": k_ms / ms_step,
+        "all_gemm_launches": {"per_step": len(prof) / args.steps, "ms_per_step": gemm_ms,
+                              "algorithmic_tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None},
         "mma_passes_per_product": passes,
         "executed_tflops": achieved * passes if achieved else None,
         "frac_executed": (achieved * passes / peak_tf) if achieved else None,

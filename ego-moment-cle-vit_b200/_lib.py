@@ -32,6 +32,10 @@ SIGNATURES = {
     "egm_version": (_I, []),
     "egm_last_error": (c_char_p, []),
     "egm_launch_count": (ctypes.c_ulonglong, []),
+    "egm_prof_enable": (None, [_I]),
+    "egm_prof_reset": (None, []),
+    "egm_prof_count": (_I, []),
+    "egm_prof_read": (_I, [_I, _P, _P, _P]),
     "egm_gpf_ldr": (_LL, [_I]),
     "egm_gpf_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_gpf_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

@@ -206,6 +206,10 @@ extern "C" {
 int egm_version(void) { return 100; }
 const char* egm_last_error(void) { return last_error(); }
 unsigned long long egm_launch_count(void) { return launch_count(); }
+void egm_prof_enable(int on) { prof_enable(on); }
+void egm_prof_reset(void) { prof_reset(); }
+int egm_prof_count(void) { return prof_count(); }
+int egm_prof_read(int i, float* ms, double* flops, int* dims) { return prof_read(i, ms, flops, dims); }
 
 // =========================================================================== GPF
 long long egm_gpf_ldr(int N) { return ((long long)N + 3) / 4 * 4; }

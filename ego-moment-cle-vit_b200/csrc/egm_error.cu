@@ -4,6 +4,10 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
 
 #include "egm_gemm.h"
 
@@ -20,5 +24,52 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional per-launch timing of the GEMM engine (C ABI: egm_prof_*) -------------------------
+// When enabled, every tcgen05 GEMM launch is bracketed by two CUDA events on its own stream; the
+// benchmark reads the durations back after synchronising. Off by default: no events, no cost.
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; double flops; int dims[6]; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::atomic<int> g_prof_on{0};
+}
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+void prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on.store(on ? 1 : 0);
+}
+void prof_reset() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+}
+int prof_begin(cudaStream_t st, double flops, const int dims[6]) {
+  ProfRec r;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  r.flops = flops;
+  for (int i = 0; i < 6; ++i) r.dims[i] = dims[i];
+  cudaEventRecord(r.e0, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_end(int id, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (id >= 0 && id < (int)g_prof.size()) cudaEventRecord(g_prof[id].e1, st);
+}
+int prof_count() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return (int)g_prof.size();
+}
+int prof_read(int i, float* ms, double* flops, int* dims) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (i < 0 || i >= (int)g_prof.size()) return -1;
+  if (cudaEventSynchronize(g_prof[i].e1) != cudaSuccess) return -2;
+  if (cudaEventElapsedTime(ms, g_prof[i].e0, g_prof[i].e1) != cudaSuccess) return -2;
+  *flops = g_prof[i].flops;
+  for (int k = 0; k < 6; ++k) dims[k] = g_prof[i].dims[k];
+  return 0;
 }
 }  // namespace egm

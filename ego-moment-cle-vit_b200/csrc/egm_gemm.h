@@ -89,4 +89,13 @@ void note_launch();                 // every kernel launch of the library calls 
 unsigned long long launch_count();
 void set_error(const char* fmt, ...);
 
+// optional per-launch timing of the tcgen05 engine (egm_error.cu; C ABI egm_prof_*)
+bool prof_enabled();
+void prof_enable(int on);
+void prof_reset();
+int prof_begin(cudaStream_t st, double flops, const int dims[6]);   // dims: M, N, K0, K1, batch, passes
+void prof_end(int id, cudaStream_t st);
+int prof_count();
+int prof_read(int i, float* ms, double* flops, int* dims);
+
 }  // namespace egm

@@ -1059,9 +1059,19 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
       p.tma_cf = 1;
     }
   }
+  int prof_id = -1;
+  if (prof_enabled()) {
+    // algorithmic flops of what is actually evaluated (skipped lower tiles are not counted)
+    double flops = 0;
+    for (int t = 0; t < g.nterms; ++t) flops += 2.0 * g.M * g.N * (double)g.t[t].K * g.batch;
+    if (p.triu_tiles) flops *= (double)p.tiles_per_img / (p.tiles_m * p.tiles_n);
+    const int dims[6] = {g.M, g.N, g.t[0].K, g.nterms > 1 ? g.t[1].K : 0, g.batch, npass};
+    prof_id = prof_begin(stream, flops, dims);
+  }
   cudaError_t le;
   if (ctas == 2) le = npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
   else le = npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
+  if (prof_id >= 0) prof_end(prof_id, stream);
   if (le != cudaSuccess) return le;
   if (g.dot_out) {
     const int per_img = p.tiles_per_img * 4 * ctas;

@@ -58,6 +58,14 @@ int egm_version(void);
 const char* egm_last_error(void);
 /* kernels launched by this library in this process so far (monotonic; bench.py's gpu_launches) */
 unsigned long long egm_launch_count(void);
+/* Optional per-launch timing of the tcgen05 GEMM engine (bench.py's roofline): while enabled,
+ * every engine launch is bracketed by two CUDA events on its own stream. egm_prof_read(i)
+ * synchronises on launch i and returns its duration, its algorithmic flops and
+ * dims = {M, N, K of term 0, K of term 1 (0 if absent), batch, MMA passes per product}. */
+void egm_prof_enable(int on);
+void egm_prof_reset(void);
+int egm_prof_count(void);
+int egm_prof_read(int i, float* ms, double* flops, int* dims);
 
 /* ---- Graph Polynomial Fusion ------------------------------------------------------------
  * a, p [B,N,D]; coef [(P+1)*(Q+1)] = softplus(alpha) on the device; G [B,N,N].

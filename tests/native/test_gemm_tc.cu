@@ -122,6 +122,7 @@ static int run_case(const Case& c) {
     E.init(c.M, c.N, c.batch, c.pad, true);
     g.E = c.e_mode == 1 ? E.planes() : E.f32();
     g.e_planes = c.e_mode == 1;
+    if (c.e_mode == 1 && c.npass != 3) g.E.p1 = nullptr;   // single-pass mode carries no lo plane
   }
   // outputs
   const long long ldp = ((c.N + 7) / 8) * 8 + c.pad;
