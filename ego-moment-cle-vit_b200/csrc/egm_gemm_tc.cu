@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses, coordinates and
+    // descriptors in uniform registers); one elected lane issues the copies.
+    {
+      const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -435,34 +438,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int n0 = tn * BN;
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
+          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t fb = full_bar(stage);
-            ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
             const int k0 = kb * BK;
+            if (issuer) {
+              ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
 #pragma unroll
-            for (int pl = 0; pl < C::kPlanes; ++pl) {
-              if (!p.a_mn[t]) {
-                ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
-              } else {
+              for (int pl = 0; pl < C::kPlanes; ++pl) {
+                if (!a_mn) {
+                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BM / 64; ++j)
-                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j, k0, bl);
-              }
-              if (!p.b_mn[t]) {
-                ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, bl);
-              } else {
+                  for (int j = 0; j < BM / 64; ++j)
+                    ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j, k0, bl);
+                }
+                if (!b_mn) {
+                  ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, bl);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                  ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk,
-                                   n0 + 64 * j, k0, bl);
+                  for (int j = 0; j < BN / 64; ++j)
+                    ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk,
+                                     n0 + 64 * j, k0, bl);
+                }
               }
             }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -470,7 +477,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (and therefore also commits) every MMA
+    {
+      const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -496,26 +505,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
+            if (issuer) {
 #pragma unroll
-            for (int kk = 0; kk < BK / UK; ++kk) {
-              const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
-              const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
-              if (NPASS == 3) {
-                const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
-                const uint64_t bl = ptx::smem_desc_sw128(sB + kTileB + kk * b_step, b_lbo, 1024);
-                ptx::mma_bf16_ss(d_tmem, al, bh, idesc, accumulate);
-                ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
-                ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
-              } else {
-                ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, accumulate);
+              for (int kk = 0; kk < BK / UK; ++kk) {
+                const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
+                const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
+                if (NPASS == 3) {
+                  const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
+                  const uint64_t bl = ptx::smem_desc_sw128(sB + kTileB + kk * b_step, b_lbo, 1024);
+                  ptx::mma_bf16_ss(d_tmem, al, bh, idesc, (kk == 0) ? accumulate : 1u);
+                  ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
+                  ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
+                } else {
+                  ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, (kk == 0) ? accumulate : 1u);
+                }
               }
-              accumulate = 1u;
+              ptx::tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
             }
-            ptx::tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+            __syncwarp();
+            accumulate = 1u;
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        ptx::tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (issuer) ptx::tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -627,7 +640,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
 
   if (warp == 0) {
     // --------------------------------------------- TMA producer (both CTAs of the pair)
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues the copies (see the 1-CTA kernel)
+    {
+      const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -639,35 +654,39 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         const int n0 = tn * BN + rank * (BN / 2);        // this CTA's 128 columns of B
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
+          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
             ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
             const uint32_t fb = ptx::mapa(full_bar(stage), 0);         // the leader's barrier
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
             const int k0 = kb * BK;
+            if (issuer) {
+              if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
 #pragma unroll
-            for (int pl = 0; pl < C::kPlanes; ++pl) {
-              if (!p.a_mn[t]) {
-                ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
-              } else {
+              for (int pl = 0; pl < C::kPlanes; ++pl) {
+                if (!a_mn) {
+                  ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BM / 64; ++j)
-                  ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk,
-                                       m0 + 64 * j, k0, bl);
-              }
-              if (!p.b_mn[t]) {
-                ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, bl);
-              } else {
+                  for (int j = 0; j < BM / 64; ++j)
+                    ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk,
+                                         m0 + 64 * j, k0, bl);
+                }
+                if (!b_mn) {
+                  ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, bl);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / 128; ++j)
-                  ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh + j * kChunk,
-                                       n0 + 64 * j, k0, bl);
+                  for (int j = 0; j < BN / 128; ++j)
+                    ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh + j * kChunk,
+                                         n0 + 64 * j, k0, bl);
+                }
               }
             }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -675,7 +694,8 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    if (leader) {
+      const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -701,26 +721,30 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
+            if (issuer) {
 #pragma unroll
-            for (int kk = 0; kk < BK / UK; ++kk) {
-              const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
-              const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
-              if (NPASS == 3) {
-                const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
-                const uint64_t bl = ptx::smem_desc_sw128(sB + kTileBh + kk * b_step, b_lbo, 1024);
-                ptx::mma_bf16_ss_2sm(d_tmem, al, bh, idesc, accumulate);
-                ptx::mma_bf16_ss_2sm(d_tmem, ah, bl, idesc, 1u);
-                ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, 1u);
-              } else {
-                ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, accumulate);
+              for (int kk = 0; kk < BK / UK; ++kk) {
+                const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
+                const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
+                if (NPASS == 3) {
+                  const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
+                  const uint64_t bl = ptx::smem_desc_sw128(sB + kTileBh + kk * b_step, b_lbo, 1024);
+                  ptx::mma_bf16_ss_2sm(d_tmem, al, bh, idesc, (kk == 0) ? accumulate : 1u);
+                  ptx::mma_bf16_ss_2sm(d_tmem, ah, bl, idesc, 1u);
+                  ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, 1u);
+                } else {
+                  ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, (kk == 0) ? accumulate : 1u);
+                }
               }
-              accumulate = 1u;
+              ptx::tc_commit_2sm(empty_bar(stage), 0x3);   // frees the slot in both CTAs
             }
-            ptx::tc_commit_2sm(empty_bar(stage), 0x3);   // frees the slot in both CTAs
+            __syncwarp();
+            accumulate = 1u;
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        ptx::tc_commit_2sm(tfull_bar(acc), 0x3);         // both CTAs' epilogues may start
+        if (issuer) ptx::tc_commit_2sm(tfull_bar(acc), 0x3);   // both CTAs' epilogues may start
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

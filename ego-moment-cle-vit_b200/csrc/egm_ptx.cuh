@@ -22,6 +22,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One lane of the (converged) warp gets `true`. Keeping control flow warp-uniform and gating
+// only the issue on this predicate lets ptxas hold addresses/descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

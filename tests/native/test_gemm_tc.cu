@@ -349,6 +349,7 @@ int main(int argc, char** argv) {
       // secondary plane output + <C,F> + alpha_b (A = M/tau and T_0 from one product)
       {"Cp2 + dot, 300x300x197 b3 x3 alpha_b",  300, 300, 3, 1, {197, 0}, {1, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0},
       {"Cp2 + dot, 200x264 b2 x1 ragged, f32",  200, 264, 2, 1, {72, 0},  {0, 0}, {1, 0}, 1, 0.5f, 0.25f, -0.5f, 1, 0, 1, 1, 8, 0, 0, 1, 1, 0},
+      {"planes addend, x1, 200x264x72 ragged", 200, 264, 2, 1, {72, 0},  {0, 0}, {1, 0}, 1, 0.5f, 0.25f, -0.5f, 1, 0, 1, 1, 8, 0, 0, 0, 0, 0},
       {"dot only U=W Zc 197x768x197 b2 x3",     197, 768, 2, 1, {197, 0}, {0, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0},
       // packed upper triangle (+ fp32 copy of the full matrix is excluded where tiles are skipped)
       {"triu packed 768^3 b2 x3 post-scaled",   768, 768, 2, 1, {768, 0}, {0, 0}, {0, 0}, 3, 1.f, 0.f, 0.f, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1},
