@@ -529,7 +529,7 @@ size_t egm_mhd_state_bytes(int B, int N, int D, int iters, int prec) {
 size_t egm_mhd_fwd_workspace(int B, int N, int D, int iters, int prec) {
   (void)iters; (void)prec;
   return pad256(w_bytes(B, N, D)) + pad256((size_t)B * 4) +
-         pad256((size_t)B * ((N + 127) / 128 + 1) * 4 * ((D + 255) / 256) * 4) + 2048;
+         pad256((size_t)B * ((N + 127) / 128 + 1) * 8 * ((D + 255) / 256) * 4) + 2048;
 }
 
 int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps,
@@ -592,7 +592,7 @@ size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec) {
   return 7 * pad256(w_bytes(B, D, D)) + 2 * pad256(w_bytes(B, N, D)) + pad256((size_t)B * N * D * 4) +
          pad256((size_t)B * N * egm_gpf_ldr(N) * 4) + pad256((size_t)B * D * 4) +
          3 * pad256((size_t)B * N * 4) + 2 * pad256((size_t)B * 4) +
-         pad256((size_t)B * 8 * 4 * ((D + 255) / 256) * ((D + 255) / 256)) + 4096;
+         pad256((size_t)B * 16 * 4 * ((D + 255) / 256) * ((D + 255) / 256)) + 4096;
 }
 
 int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float* Z, const float* G,
@@ -627,7 +627,7 @@ int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float
   float* dotA = static_cast<float*>(ar.take((size_t)B * 4));
   float* dtau = static_cast<float*>(ar.take((size_t)B * 4));
   const int tl = (D + 255) / 256;
-  float* dot_ws = static_cast<float*>(ar.take((size_t)B * 8 * 4 * tl * tl));
+  float* dot_ws = static_cast<float*>(ar.take((size_t)B * 16 * 4 * tl * tl));
   EGM_REQUIRE(buf[5].base && dAw.base && V1.base && V2.base && dZc && dW && dmu && dw && ds && dt && dotA &&
                   dtau && dot_ws,
               EGM_ERR_WORKSPACE, "egm_mhd_bwd: workspace %zu < %zu", ws_bytes,

@@ -44,10 +44,11 @@ constexpr int UK = 16;         // K per tcgen05.mma (bf16)
 constexpr int kTileA = BM * BK * 2;   // 16 KiB per plane
 constexpr int kTileB = BN * BK * 2;   // 32 KiB per plane
 constexpr int kChunk = BK * 128;      // one MN-major TMA box: 64 K-rows x 128 B = 8 KiB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;          // two per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kTmemCols = 512;        // two 256-column accumulators
-constexpr int kEpiWarpBytes = 8192;   // per epilogue warp: 2 slots x (32 rows x 128 B)
-constexpr int kEpiBytes = 4 * kEpiWarpBytes;
+constexpr int kEpiWarpBytes = 4096;   // per epilogue warp: one staging slot (32 rows x 128 B)
+constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
 
 struct alignas(64) TcParams {
   CUtensorMap tm[2][4];  // [term][A_hi, A_lo, B_hi, B_lo]
@@ -103,11 +104,6 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
-         (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
-}
-
 // tile index within one image -> (row tile, column tile). With triu_tiles only the tiles that
 // contain at least one element on or above the diagonal are enumerated (row-tile major).
 __device__ __forceinline__ void tile_coords(const TcParams& p, int r, int& tm, int& tn) {
@@ -182,36 +178,51 @@ __device__ __forceinline__ void load_chunk(const void* P0, const void* P1, int m
   }
 }
 
+// two floats -> packed bf16x2 (round to nearest even); `lo` lands in bits [0,16)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // one lane's row of a 32 x 32 chunk -> bf16 hi/lo staging slot (rows of 64 B, 64B swizzle)
 __device__ __forceinline__ void stage_planes(uint32_t buf, int lane, const float (&o)[32], bool has_lo) {
   const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint32_t hw[4], lw[4];
+    uint32_t hw[4];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(o[j * 8 + 2 * w], h0, l0);
-      split_bf16(o[j * 8 + 2 * w + 1], h1, l1);
-      hw[w] = pack2(h0, h1);
-      lw[w] = pack2(l0, l1);
-    }
+    for (int w = 0; w < 4; ++w) hw[w] = cvt_bf16x2(o[j * 8 + 2 * w + 1], o[j * 8 + 2 * w]);
     const uint32_t off = lane * 64 + ((j ^ sw) << 4);
     ptx::sts128(buf + off, hw[0], hw[1], hw[2], hw[3]);
-    if (has_lo) ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
+    if (has_lo) {
+      uint32_t lw[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        lw[w] = cvt_bf16x2(o[j * 8 + 2 * w + 1] - __uint_as_float(hw[w] & 0xFFFF0000u),
+                           o[j * 8 + 2 * w] - __uint_as_float(hw[w] << 16));
+      ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
+    }
   }
 }
 
-// Plane output of one chunk: TMA store through the staging slot when the layout allows it
-// (full-line writes, no LSU traffic, ragged edges clipped by the tensor map), else scalar.
+// Plane output of one chunk: TMA store through the warp's staging slot when the layout allows
+// it (full-line writes, no LSU traffic, ragged edges clipped by the tensor map), else scalar.
 __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, const CUtensorMap* tmh,
                                              const CUtensorMap* tml, __nv_bfloat16* hi,
                                              __nv_bfloat16* lo, long long ld, long long bs, int b,
                                              int row, int row0, int col0, int ncols, bool row_ok,
-                                             int lane, uint32_t stage_smem, int& slot) {
+                                             int lane, uint32_t buf, int& half_slot) {
   if (tma) {
-    const uint32_t buf = stage_smem + slot * 4096;
-    if (lane == 0) ptx::bulk_wait_read<1>();   // the store that used this slot has drained
+    // hi + lo fill the 4 KiB slot; a hi-only store (single-pass mode) needs half of it, so two
+    // stores can be in flight and the wait below almost never blocks
+    if (lo) {
+      if (lane == 0) ptx::bulk_wait_read<0>();   // the store that used this slot has drained
+    } else {
+      buf += half_slot * 2048;
+      half_slot ^= 1;
+      if (lane == 0) ptx::bulk_wait_read<1>();
+    }
     __syncwarp();
     stage_planes(buf, lane, o, lo != nullptr);
     ptx::fence_proxy_async_smem();
@@ -221,7 +232,6 @@ __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, con
       if (lo) ptx::tma_store_3d(tml, buf + 2048, col0, row0, b);
       ptx::bulk_commit();
     }
-    slot ^= 1;
   } else if (row_ok) {
     __nv_bfloat16* ch = hi + b * bs + (long long)row * ld + col0;
     __nv_bfloat16* cl = lo ? lo + b * bs + (long long)row * ld + col0 : nullptr;
@@ -239,33 +249,41 @@ __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, con
 // Epilogue of one accumulator tile for one warp: TMEM -> registers -> alpha*acc + beta*I +
 // gamma*E -> bf16 hi/lo planes and/or fp32 (+ optional secondary planes, <C,F> partial, packed
 // upper triangle). `t_addr` addresses this warp's 32 TMEM lanes, `row0` is the warp's first
-// output row, `n0` the first output column of the 256-wide tile. Two 4 KiB staging slots per
-// warp alternate (`slot`), so the store of chunk c overlaps the TMEM read of chunk c+1.
+// output row (a multiple of 32), `n0` the first output column of the 256-wide tile; the warp
+// handles the 32-column chunks [c_begin, c_end). The TMEM load of chunk c+1 is in flight while
+// chunk c is processed; one 4 KiB staging slot per warp (`buf`) feeds the TMA stores
+// (`half_slot`: which 2 KiB half the next hi-only store uses, carried across tiles).
 // Returns this lane's share of <C, F>.
 __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_addr, int b, int row0,
-                                               int lane, int n0, uint32_t stage_smem, int& slot) {
+                                               int lane, int n0, uint32_t buf, int c_begin, int c_end,
+                                               int& half_slot) {
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const float a_eff = p.alpha * (p.alpha_b ? __ldg(p.alpha_b + b) : 1.f);
   const float beta = p.beta_eye * (p.beta_b ? __ldg(p.beta_b + b) : 1.f);
   const float gamma = p.gamma * (p.gamma_b ? __ldg(p.gamma_b + b) : 1.f);
   float dsum = 0.f;
+  // warp-uniform chunk range: stop at N, and skip chunks entirely below the diagonal for X
+  while (c_end > c_begin && n0 + (c_end - 1) * 32 >= p.N) --c_end;
+  if (p.X_hi)
+    while (c_begin < c_end && n0 + c_begin * 32 + 31 < row0) ++c_begin;
+  if (c_begin >= c_end) return 0.f;
+  uint32_t v[32];
+  ptx::tmem_ld_32x32(t_addr + c_begin * 32, v);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int col0 = n0 + c * 32;
-    if (col0 >= p.N) break;  // warp-uniform
-    if (p.X_hi && col0 + 31 < row0) continue;  // chunk entirely below the diagonal (warp-uniform)
-    uint32_t v[32];
-    ptx::tmem_ld_32x32(t_addr + c * 32, v);
     ptx::tmem_ld_wait();
     float o[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = a_eff * __uint_as_float(v[j]);
-    const int d = row - col0;  // diagonal position inside this chunk, if any
-    if (beta != 0.f && d >= 0 && d < 32) {
+    if (c + 1 < c_end) ptx::tmem_ld_32x32(t_addr + (c + 1) * 32, v);   // overlaps the work below
+    // rows and columns of a chunk are both 32-aligned: the diagonal crosses it iff col0 == row0
+    const bool diag = (col0 == row0);
+    if (beta != 0.f && diag) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j == d) o[j] += beta;
+        if (j == lane) o[j] += beta;
     }
     if (p.e_mode && row_ok) {
       float e[32];
@@ -281,22 +299,21 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
     }
     if (p.Cp_hi)
       store_planes(o, p.tma_cp != 0, &p.tmC[0], &p.tmC[1], p.Cp_hi, p.Cp_lo, p.ldCp, p.bsCp, b, row, row0,
-                   col0, p.N, row_ok, lane, stage_smem, slot);
+                   col0, p.N, row_ok, lane, buf, half_slot);
     if (p.C2_hi) {
       float o2[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) o2[j] = p.c2_scale * o[j];
-      if (p.c2_eye != 0.f && d >= 0 && d < 32) {
+      if (p.c2_eye != 0.f && diag) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j == d) o2[j] += p.c2_eye;
+          if (j == lane) o2[j] += p.c2_eye;
       }
       store_planes(o2, p.tma_c2 != 0, &p.tmC2[0], &p.tmC2[1], p.C2_hi, p.C2_lo, p.ldC2, p.bsC2, b, row,
-                   row0, col0, p.N, row_ok, lane, stage_smem, slot);
+                   row0, col0, p.N, row_ok, lane, buf, half_slot);
     }
     if (p.X_hi) {
       // packed upper triangle: stage the chunk, then every row leaves as one contiguous run
-      const uint32_t buf = stage_smem + slot * 4096;
       __syncwarp();
       stage_planes(buf, lane, o, p.X_lo != nullptr);
       __syncwarp();
@@ -312,12 +329,10 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
           if (p.X_lo) p.X_lo[idx] = __ushort_as_bfloat16(ptx::lds16(buf + 2048 + off));
         }
       }
-      slot ^= 1;
     }
     if (p.Cf) {
       if (p.tma_cf) {
-        const uint32_t buf = stage_smem + slot * 4096;
-        if (lane == 0) ptx::bulk_wait_read<1>();
+        if (lane == 0) ptx::bulk_wait_read<0>();
         __syncwarp();
         const uint32_t sw = lane & 7;              // 128B swizzle: 16B chunk ^= addr bits [7,10)
 #pragma unroll
@@ -331,7 +346,6 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
           ptx::tma_store_3d(&p.tmC[2], buf, col0, row0, b);
           ptx::bulk_commit();
         }
-        slot ^= 1;
       } else if (row_ok) {
         float* cf = p.Cf + b * p.bsCf + (long long)row * p.ldCf + col0;
         if (col0 + 32 <= p.N && (p.ldCf & 3) == 0) {
@@ -405,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        ptx::mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
       }
       ptx::fence_barrier_init();
     }
@@ -535,8 +549,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int slot = 0;
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns
+    const int cb = half * (BN / 64), ce = cb + BN / 64;
+    int half_slot = 0;                  // persists across tiles: a store may still be in flight
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -549,8 +565,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
-                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
-      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * 4 + q);
+                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
+      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * kEpiWarps + (warp - 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -620,7 +636,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);   // multicast commit
-        ptx::mbar_init(tempty_bar(a), 8);  // used in the leader: 4 epilogue warps x 2 CTAs
+        ptx::mbar_init(tempty_bar(a), 2 * kEpiWarps);  // used in the leader: epilogue warps x 2 CTAs
       }
       ptx::fence_barrier_init();
     }
@@ -752,7 +768,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   } else {
     // ----------------------------------------------------- epilogue (both CTAs, own rows)
     const int q = warp & 3;
-    int slot = 0;
+    const int half = (warp - 2) >> 2;
+    const int cb = half * (BN / 64), ce = cb + BN / 64;
+    int half_slot = 0;                  // persists across tiles: a store may still be in flight
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -765,8 +783,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
-                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, slot);
-      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * 8 + rank * 4 + q);
+                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
+      if (p.dot_ws)
+        write_dot_partial(p, ds, lane, (long long)tile * (2 * kEpiWarps) + rank * kEpiWarps + (warp - 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -945,7 +964,7 @@ size_t gemm_tc_dot_ws_floats(const GemmProblem& g) {
   const int ctas = tc_ctas();
   const int tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   const int tiles_n = (g.N + BN - 1) / BN;
-  return (size_t)g.batch * tiles_m * tiles_n * 4 * ctas;
+  return (size_t)g.batch * tiles_m * tiles_n * kEpiWarps * ctas;
 }
 
 cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
@@ -1098,7 +1117,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   if (prof_id >= 0) prof_end(prof_id, stream);
   if (le != cudaSuccess) return le;
   if (g.dot_out) {
-    const int per_img = p.tiles_per_img * 4 * ctas;
+    const int per_img = p.tiles_per_img * kEpiWarps * ctas;
     dot_reduce_kernel<<<(g.batch + 7) / 8, 256, 0, stream>>>(g.dot_ws, per_img, g.batch, g.dot_out);
     note_launch();
     le = cudaGetLastError();

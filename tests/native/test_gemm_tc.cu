@@ -324,8 +324,48 @@ static void bench(int D, int batch, int npass, int tA, int tB) {
   A.free_(); B.free_();
 }
 
+// time vs K at fixed output shape: slope = per-k-block time, intercept = per-tile overhead
+static void sweep(int D, int batch, int npass) {
+  const int Ks[] = {128, 256, 512, 768, 1024, 1536, 2048};
+  for (int K : Ks) {
+    size_t pa = (size_t)D * K, pc = (size_t)D * D;
+    __nv_bfloat16 *ah, *al, *bh, *bl, *ch, *cl;
+    CK(cudaMalloc(&ah, pa * batch * 2)); CK(cudaMalloc(&al, pa * batch * 2));
+    CK(cudaMalloc(&bh, pa * batch * 2)); CK(cudaMalloc(&bl, pa * batch * 2));
+    CK(cudaMalloc(&ch, pc * batch * 2)); CK(cudaMalloc(&cl, pc * batch * 2));
+    CK(cudaMemset(ah, 0, pa * batch * 2)); CK(cudaMemset(al, 0, pa * batch * 2));
+    CK(cudaMemset(bh, 0, pa * batch * 2)); CK(cudaMemset(bl, 0, pa * batch * 2));
+    GemmProblem g;
+    g.M = D; g.N = D; g.batch = batch; g.nterms = 1;
+    g.t[0].A.p0 = ah; g.t[0].A.p1 = al; g.t[0].A.rows = D; g.t[0].A.cols = K; g.t[0].A.ld = K; g.t[0].A.bstride = pa;
+    g.t[0].B.p0 = bh; g.t[0].B.p1 = bl; g.t[0].B.rows = K; g.t[0].B.cols = D; g.t[0].B.ld = D; g.t[0].B.bstride = pa;
+    g.t[0].transA = 0; g.t[0].transB = 0; g.t[0].K = K;
+    g.Cp.p0 = ch; g.Cp.p1 = npass == 3 ? cl : nullptr; g.Cp.rows = D; g.Cp.cols = D; g.Cp.ld = D; g.Cp.bstride = pc;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) CK(egm::gemm_tc(g, npass, 0));
+    CK(cudaDeviceSynchronize());
+    const int iters = 10;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(egm::gemm_tc(g, npass, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+    const double tiles = (double)((D + 255) / 256) * ((D + 255) / 256) * batch;
+    const double us_tile = ms * 1e3 / (tiles / 74.0);
+    printf("[sweep] D=%d batch=%d npass=%d K=%4d : %.3f ms  %.2f us/tile/pair  %.1f TFLOP/s executed\n", D, batch,
+           npass, K, ms, us_tile, 2.0 * D * D * K * batch * npass / ms * 1e-9);
+    fflush(stdout);
+    cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl); cudaFree(ch); cudaFree(cl);
+  }
+}
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "sweep")) {
+    sweep(768, 128, 1);
+    sweep(768, 128, 3);
+    return 0;
+  }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   int fails = 0;
