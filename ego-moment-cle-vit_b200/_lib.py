@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libegm_b200.so")
 
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+MHD_SYMMETRIC_GRAPH = 1      # EGM_MHD_SYMMETRIC_GRAPH
 _PREC_NAMES = {"fp32_simt": PREC_FP32_SIMT, "fp32": PREC_BF16X3, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lock = threading.Lock()
@@ -58,9 +59,9 @@ SIGNATURES = {
     "egm_mlr_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
     "egm_mhd_state_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "egm_mhd_fwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
-    "egm_mhd_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "egm_mhd_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_mhd_bwd_workspace": (_Z, [_I, _I, _I, _I, _I]),
-    "egm_mhd_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _Z, _P]),
+    "egm_mhd_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _I, _P, _Z, _P]),
     "egm_rowdot_bias": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "egm_linear_state_bytes": (_Z, [_I, _I, _I, _I]),
     "egm_linear_fwd_workspace": (_Z, [_I, _I, _I, _I]),

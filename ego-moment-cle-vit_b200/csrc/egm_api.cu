@@ -38,13 +38,22 @@ struct NsState {
 //   Z_1 = T_0 A; k = 1..K-1: T_k = 1.5 I - 0.5 Z_k Y_k, Y_{k+1} = Y_k T_k, Z_{k+1} = T_k Z_k;
 // the last product leaves as  post * Y_{K-1} T_{K-1}  either in fp32 (O) or as the packed upper
 // triangle in bf16 planes (X: the operand of second_net's Linear; lower tiles are not computed).
-int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, const W* X, cudaStream_t st) {
+// `sym`: A is symmetric, so every matrix of the chain is; all of them are kept in the engine's
+// symmetric block storage (GemmTerm::symA) and only the upper tiles of each product are evaluated.
+int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, const W* X, cudaStream_t st,
+                    bool sym = false) {
   const int B = S.B, D = S.D, K = S.K;
   const long long dd = (long long)D * D;
+  auto prod = [&](const W& a, const W& b) {
+    GemmTerm t = term(a, 0, b, 0, D, prec);
+    t.symA = t.symB = sym ? 1 : 0;
+    return t;
+  };
   {
     GemmProblem g;  // Z_1 = T_0 A
     g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-    g.t[0] = term(S.T(0), 0, S.A(), 0, D, prec);
+    g.t[0] = prod(S.T(0), S.A());
+    g.sym_out = sym;
     out_w(g, S.Z(1), prec);
     EGM_CUDA(run_gemm(g, prec, st));
   }
@@ -52,8 +61,9 @@ int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, con
     {
       GemmProblem g;  // T_k = 1.5 I - 0.5 Z_k Y_k
       g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(S.Z(k), 0, S.Y(k), 0, D, prec);
+      g.t[0] = prod(S.Z(k), S.Y(k));
       g.alpha = -0.5f; g.beta_eye = 1.5f;
+      g.sym_out = sym;
       out_w(g, S.T(k), prec);
       EGM_CUDA(run_gemm(g, prec, st));
     }
@@ -61,21 +71,23 @@ int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, con
       {
         GemmProblem g;  // Y_{k+1} = Y_k T_k
         g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-        g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+        g.t[0] = prod(S.Y(k), S.T(k));
+        g.sym_out = sym;
         out_w(g, S.Y(k + 1), prec);
         EGM_CUDA(run_gemm(g, prec, st));
       }
       {
         GemmProblem g;  // Z_{k+1} = T_k Z_k
         g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-        g.t[0] = term(S.T(k), 0, S.Z(k), 0, D, prec);
+        g.t[0] = prod(S.T(k), S.Z(k));
+        g.sym_out = sym;
         out_w(g, S.Z(k + 1), prec);
         EGM_CUDA(run_gemm(g, prec, st));
       }
     } else {
       GemmProblem g;  // O = post * Y_{K-1} T_{K-1}
       g.M = D; g.N = D; g.batch = B; g.nterms = 1;
-      g.t[0] = term(S.Y(k), 0, S.T(k), 0, D, prec);
+      g.t[0] = prod(S.Y(k), S.T(k));
       g.alpha_b = post;
       if (X) {
         g.X = w_mat(*X, prec);
@@ -165,18 +177,90 @@ int ns_products_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cuda
 }
 
 
+// Backward of the chain for a SYMMETRIC A (K >= 2), evaluated as a forward tangent.
+// Y_K is a fixed polynomial in A, so its Frechet derivative L(A, .) is self-adjoint for symmetric A:
+// the gradient L^*(A, dY_K) equals the tangent L(A, dY_K). It also commutes with transposition, so
+// the symmetric part of dA (all the rest of the path needs when the graph is symmetric) is the
+// tangent in the direction sym(dY_K) - and along a symmetric direction every tangent Y'_k, Z'_k,
+// T'_k is itself symmetric: each of the 3K-3 two-term products below evaluates its upper tiles only.
+//   Y'_1 = T'_0 = -E/2,  Z'_1 = T'_0 A + T_0 E = -3 Y'_1 + (Y'_1 A + A Y'_1)
+//   T'_k = -(Z'_k Y_k + Z_k Y'_k)/2,  Y'_{k+1} = Y'_k T_k + Y_k T'_k,  Z'_{k+1} = T'_k Z_k + T_k Z'_k
+// buf[0] holds Y'_1 = -post*sym(dO)/2 on entry (symmetric block storage); buf[1..4] are scratch.
+// The result dA = Y'_K goes to fin.dA_w with <dA, A> in fin.dot_out.
+int ns_tangent_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+  const int B = S.B, D = S.D, K = S.K;
+  W Yd = buf[0], Zd = buf[1], Td = buf[2], Ydn = buf[3], Zdn = buf[4];
+  auto two = [&](GemmProblem& g, const W& a0, const W& b0, const W& a1, const W& b1) {
+    g.M = D; g.N = D; g.batch = B; g.nterms = 2;
+    g.t[0] = term(a0, 0, b0, 0, D, prec);
+    g.t[1] = term(a1, 0, b1, 0, D, prec);
+    g.t[0].symA = g.t[0].symB = g.t[1].symA = g.t[1].symB = 1;
+    g.sym_out = 1;
+  };
+  {
+    GemmProblem g;  // Z'_1 = -3 Y'_1 + Y'_1 A + A Y'_1
+    two(g, Yd, S.A(), S.A(), Yd);
+    addend_w(g, Yd, -3.f, prec);
+    out_w(g, Zd, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+  }
+  for (int k = 1; k <= K - 1; ++k) {
+    {
+      GemmProblem g;  // T'_k = -(Z'_k Y_k + Z_k Y'_k)/2
+      two(g, Zd, S.Y(k), S.Z(k), Yd);
+      g.alpha = -0.5f;
+      out_w(g, Td, prec);
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+    if (k < K - 1) {
+      {
+        GemmProblem g;  // Y'_{k+1} = Y'_k T_k + Y_k T'_k
+        two(g, Yd, S.T(k), S.Y(k), Td);
+        out_w(g, Ydn, prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      {
+        GemmProblem g;  // Z'_{k+1} = T'_k Z_k + T_k Z'_k
+        two(g, Td, S.Z(k), S.T(k), Zd);
+        out_w(g, Zdn, prec);
+        EGM_CUDA(run_gemm(g, prec, st));
+      }
+      W tmp = Yd; Yd = Ydn; Ydn = tmp;
+      tmp = Zd; Zd = Zdn; Zdn = tmp;
+    } else {
+      GemmProblem g;  // dA = Y'_K = Y'_{K-1} T_{K-1} + Y_{K-1} T'_{K-1}
+      two(g, Yd, S.T(k), S.Y(k), Td);
+      out_w(g, *fin.dA_w, prec);
+      g.F = w_mat(S.A(), prec);
+      g.f_planes = 1;
+      g.dot_out = fin.dot_out;
+      g.dot_ws = fin.dot_ws;
+      EGM_CUDA(run_gemm(g, prec, st));
+    }
+  }
+  return EGM_OK;
+}
+
+
 // Tail of the pooling backward given V1 = Zc dM^T and V2 = Zc dM:
 //   dZc = Wn V1 + Wn^T V2, dW = V2 Zc^T, then centring / weighted mean / degree normalisation.
 int pool_bwd_tail(const W& Wn, const W& Zc, const W& V1, const W& V2, const float* du, const float* Z,
                   const float* G, const float* u, const float* vecs, const float* mu, int B, int N, int D,
                   float eps, float* dZc, float* dW, long long ldW, float* dmu, float* dw, float* ds,
-                  float* dt, float* dZ, float* dG, int prec, cudaStream_t st) {
+                  float* dt, float* dZ, float* dG, int prec, cudaStream_t st, bool sym = false) {
   const float* s = vecs;
   const float* deg = vecs + (size_t)B * N;
   const float* w = vecs + (size_t)2 * B * N;
   const float* t = vecs + (size_t)4 * B * N;
   const float* sw = t + B;
-  {
+  if (sym) {
+    GemmProblem g;  // symmetric graph and dM: V1 == V2 and Wn == Wn^T, dZc = 2 Wn V
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Wn, 0, V1, 0, N, prec);
+    g.alpha = 2.f;
+    g.Cf = f32_mat(dZc, N, D, D, (long long)N * D);
+    EGM_CUDA(run_gemm(g, prec, st));
+  } else {
     GemmProblem g;  // dZc = Wn V1 + Wn^T V2
     g.M = N; g.N = D; g.batch = B; g.nterms = 2;
     g.t[0] = term(Wn, 0, V1, 0, N, prec);
@@ -532,9 +616,10 @@ size_t egm_mhd_fwd_workspace(int B, int N, int D, int iters, int prec) {
          pad256((size_t)B * ((N + 127) / 128 + 1) * 8 * ((D + 255) / 256) * 4) + 2048;
 }
 
-int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps,
+int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps, int flags,
                 void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
                 void* ws, size_t ws_bytes, egm_stream_t stream) {
+  const bool sym = (flags & EGM_MHD_SYMMETRIC_GRAPH) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
               "egm_mhd_fwd: tensor-core precision modes only (got %d)", prec);
@@ -576,6 +661,7 @@ int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, 
     g.M = D; g.N = D; g.batch = B; g.nterms = 1;
     g.t[0] = term(Zc, 1, U, 0, N, prec);
     g.alpha_b = inv;
+    g.sym_out = sym;   // Zc^T Wn Zc is symmetric when the graph is
     out_w(g, S.A(), prec);
     g.Cp2 = w_mat(S.T(0), prec);
     g.c2_scale = -0.5f; g.c2_eye = 1.5f;
@@ -584,7 +670,7 @@ int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, 
   const long long L = (long long)D * (D + 1) / 2;
   W X;
   X.base = x_planes; X.rows = B; X.cols = (int)L; X.ld = w_ld((int)L); X.batch = 1;
-  return ns_products_fwd(S, prec, post, nullptr, &X, st);
+  return ns_products_fwd(S, prec, post, nullptr, &X, st, sym);
 }
 
 size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec) {
@@ -597,8 +683,9 @@ size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec) {
 
 int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float* Z, const float* G,
                 const float* u, const float* vecs, const float* mu, const float* scal, const void* state,
-                int B, int N, int D, int iters, float eps, float* dZ, float* dG, int prec, void* ws,
-                size_t ws_bytes, egm_stream_t stream) {
+                int B, int N, int D, int iters, float eps, int flags, float* dZ, float* dG, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream) {
+  const bool sym = (flags & EGM_MHD_SYMMETRIC_GRAPH) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec == PREC_BF16X3 || prec == PREC_BF16, EGM_ERR_ARG,
               "egm_mhd_bwd: tensor-core precision modes only (got %d)", prec);
@@ -635,12 +722,34 @@ int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float
   const float* inv = scal + B;
   const float* post = scal + 2 * B;
   const long long L = (long long)D * (D + 1) / 2;
-  k::triu_unpack_planes(dv, L, B, D, post, buf[0], nullptr, prec, st);   // dY_K = post * dO
-  EGM_LAUNCHED();
   NsFinal fin;
   fin.dA_w = &dAw;
   fin.dot_out = dotA;
   fin.dot_ws = dot_ws;
+  if (sym) {
+    // symmetric graph: sym(dA) by the tangent chain (upper tiles only), then dM = inv dA + dtau I is
+    // symmetric, V1 == V2, and the dG returned is the reference's plus a skew-symmetric matrix -
+    // which every symmetric-graph producer (GraphPolynomialFusion's symmetrisation) annihilates
+    k::triu_unpack_sym_planes(dv, L, B, D, post, -0.5f, buf[0], prec, st);   // Y'_1 = -post sym(dO)/2
+    EGM_LAUNCHED();
+    const int rc = ns_tangent_bwd(S, prec, buf, fin, st);
+    if (rc != EGM_OK) return rc;
+    k::mh_dtau(scal, B, dotO, dotA, dtau, st);
+    EGM_LAUNCHED();
+    GemmProblem g;  // V = Zc dM = inv Zc dA + dtau Zc
+    g.M = N; g.N = D; g.batch = B; g.nterms = 1;
+    g.t[0] = term(Zc, 0, dAw, 0, D, prec);
+    g.t[0].symB = 1;
+    g.alpha_b = inv;
+    addend_w(g, Zc, 1.f, prec);
+    g.gamma_b = dtau;
+    out_w(g, V1, prec);
+    EGM_CUDA(run_gemm(g, prec, st));
+    return pool_bwd_tail(Wn, Zc, V1, V1, du, Z, G, u, vecs, mu, B, N, D, eps, dZc, dW, ldW, dmu, dw, ds, dt,
+                         dZ, dG, prec, st, true);
+  }
+  k::triu_unpack_planes(dv, L, B, D, post, buf[0], nullptr, prec, st);   // dY_K = post * dO
+  EGM_LAUNCHED();
   const int rc = ns_products_bwd(S, prec, buf, fin, st);
   if (rc != EGM_OK) return rc;
   k::mh_dtau(scal, B, dotO, dotA, dtau, st);

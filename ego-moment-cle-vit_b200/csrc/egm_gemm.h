@@ -39,6 +39,13 @@ struct GemmTerm {
   Mat B;       // op(B) is K x N : stored [K,N] (transB = 0) or [N,K] (transB = 1)
   int transB = 0;
   int K = 0;
+  // tcgen05 engine only: the operand is a SYMMETRIC square matrix of which only the upper
+  // 256 x 256 blocks (block column >= block row, diagonal blocks complete) are stored - the
+  // layout a `sym_out` product writes. Reads that fall into an absent block are redirected to
+  // the mirrored block with the operand's major-ness flipped in the UMMA descriptor, so no
+  // transpose pass and no mirrored store ever happens. transA / transB are ignored.
+  int symA = 0;
+  int symB = 0;
 };
 
 struct GemmProblem {
@@ -73,6 +80,10 @@ struct GemmProblem {
   // X.p0/p1[b * X.ld + i*N - i(i-1)/2 + j - i] = C[b][i][j], j >= i. Tiles strictly below the
   // diagonal are not computed at all. Excludes Cp / Cp2.
   Mat X;
+  // the result is symmetric (M == N): only tiles that touch the upper 256 x 256 blocks are
+  // computed and stored (6 of 9 at D = 768); consumers read it back through symA / symB.
+  // With dot_out, off-diagonal blocks count twice. E and F are read in the same upper blocks.
+  int sym_out = 0;
 };
 
 // floats of workspace `dot_ws` must provide for problem g (0 when no dot is requested)

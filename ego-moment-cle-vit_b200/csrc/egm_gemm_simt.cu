@@ -99,6 +99,10 @@ cudaError_t gemm_simt(const GemmProblem& g, cudaStream_t stream) {
     set_error("gemm_simt: needs an fp32 output and 1..2 terms");
     return cudaErrorInvalidValue;
   }
+  if (g.sym_out || g.t[0].symA || g.t[0].symB || (g.nterms > 1 && (g.t[1].symA || g.t[1].symB))) {
+    set_error("gemm_simt: symmetric block storage is a tcgen05-engine format");
+    return cudaErrorInvalidValue;
+  }
   SimtParams p = {};
   for (int t = 0; t < g.nterms; ++t) {
     p.A[t] = static_cast<const float*>(g.t[t].A.p0);

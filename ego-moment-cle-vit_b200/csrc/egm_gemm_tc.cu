@@ -58,6 +58,8 @@ struct alignas(64) TcParams {
   int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
+  int a_sym[2], b_sym[2];  // operand stored as the upper 256-blocks of a symmetric matrix
+  int sym_out;           // symmetric result: upper tiles only, off-diagonal dot partials x2
   int tiles_m, tiles_n;
   int tiles_per_img;     // tiles_m * tiles_n, or the upper-triangular subset (triu_tiles)
   int triu_tiles;        // enumerate only tiles that touch j >= i
@@ -121,6 +123,12 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int r, int& tm, i
     ++tm;
   }
 }
+
+// Symmetric operand kept as its upper 256 x 256 blocks: major-ness of the load that fetches the
+// logical block (rows r0.., K columns k0..) of an A operand / (K rows k0.., columns c0..) of a B
+// operand. A block that is absent is read from its mirror image, i.e. with the other major-ness.
+__device__ __forceinline__ int sym_a_mn(int r0, int k0) { return (k0 >> 8) < (r0 >> 8) ? 1 : 0; }
+__device__ __forceinline__ int sym_b_mn(int k0, int c0) { return (c0 >> 8) >= (k0 >> 8) ? 1 : 0; }
 
 // 32 consecutive elements of row `row` (columns col0..col0+31) of a batched matrix stored as
 // bf16 hi(/lo) planes (mode 1) or fp32 (mode 2); columns >= ncols read as zero.
@@ -452,7 +460,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int n0 = tn * BN;
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
-          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
+          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
+          const int a_kboxes = a_sym ? BM / 64 : 1;   // symmetric operands use 64-row boxes in
+          const int b_kboxes = b_sym ? BN / 64 : 1;   // both major-nesses (one tensor map)
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
@@ -462,19 +472,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
             const int k0 = kb * BK;
+            const int a_mn = a_sym ? sym_a_mn(m0, k0) : p.a_mn[t];
+            const int b_mn = b_sym ? sym_b_mn(k0, n0) : p.b_mn[t];
             if (issuer) {
               ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
 #pragma unroll
               for (int pl = 0; pl < C::kPlanes; ++pl) {
                 if (!a_mn) {
-                  ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
+                  for (int j = 0; j < a_kboxes; ++j)
+                    ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, k0, m0 + 64 * j, bl);
                 } else {
 #pragma unroll
                   for (int j = 0; j < BM / 64; ++j)
                     ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j, k0, bl);
                 }
                 if (!b_mn) {
-                  ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB, k0, n0, bl);
+                  for (int j = 0; j < b_kboxes; ++j)
+                    ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk, k0, n0 + 64 * j, bl);
                 } else {
 #pragma unroll
                   for (int j = 0; j < BN / 64; ++j)
@@ -500,21 +514,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int bt = tile / tiles_per_img;
+        int tm, tn;
+        tile_coords(p, tile - bt * tiles_per_img, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BN;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
         for (int t = 0; t < p.nterms; ++t) {
-          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
-          const uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, a_mn, b_mn);
-          const uint32_t a_step = a_mn ? 2048u : 32u;   // bytes per 16-wide K step
-          const uint32_t b_step = b_mn ? 2048u : 32u;
-          const uint32_t a_lbo = a_mn ? kChunk : 0u;
-          const uint32_t b_lbo = b_mn ? kChunk : 0u;
+          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)bt * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(bt + 1) * nkb_all / p.splits) : nkb_all;
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            const int a_mn = a_sym ? sym_a_mn(m0, kb * BK) : p.a_mn[t];
+            const int b_mn = b_sym ? sym_b_mn(kb * BK, n0) : p.b_mn[t];
+            const uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, a_mn, b_mn);
+            const uint32_t a_step = a_mn ? 2048u : 32u;   // bytes per 16-wide K step
+            const uint32_t b_step = b_mn ? 2048u : 32u;
+            const uint32_t a_lbo = a_mn ? kChunk : 0u;
+            const uint32_t b_lbo = b_mn ? kChunk : 0u;
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
@@ -566,7 +585,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       ptx::tc_fence_after();
       const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
                                      m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
-      if (p.dot_ws) write_dot_partial(p, ds, lane, (long long)tile * kEpiWarps + (warp - 2));
+      if (p.dot_ws)
+        write_dot_partial(p, (p.sym_out && (n0 >> 8) > (m0 >> 8)) ? 2.f * ds : ds, lane,
+                          (long long)tile * kEpiWarps + (warp - 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
@@ -670,7 +691,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         const int n0 = tn * BN + rank * (BN / 2);        // this CTA's 128 columns of B
         const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
         for (int t = 0; t < p.nterms; ++t) {
-          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
+          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
+          const int a_kboxes = a_sym ? BM / 64 : 1;        // symmetric operands: 64-row boxes in
+          const int b_kboxes = b_sym ? BN / 128 : 1;       // both major-nesses (one tensor map)
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
@@ -680,12 +703,16 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kPlanes * kTileA;
             const int k0 = kb * BK;
+            // both CTAs of the pair sit in the same 256-block of rows / columns: same decision
+            const int a_mn = a_sym ? sym_a_mn(m0, k0) : p.a_mn[t];
+            const int b_mn = b_sym ? sym_b_mn(k0, n0) : p.b_mn[t];
             if (issuer) {
               if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
 #pragma unroll
               for (int pl = 0; pl < C::kPlanes; ++pl) {
                 if (!a_mn) {
-                  ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA, k0, m0, bl);
+                  for (int j = 0; j < a_kboxes; ++j)
+                    ptx::tma_load_3d_2sm(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, k0, m0 + 64 * j, bl);
                 } else {
 #pragma unroll
                   for (int j = 0; j < BM / 64; ++j)
@@ -693,7 +720,8 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
                                          m0 + 64 * j, k0, bl);
                 }
                 if (!b_mn) {
-                  ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh, k0, n0, bl);
+                  for (int j = 0; j < b_kboxes; ++j)
+                    ptx::tma_load_3d_2sm(&p.tm[t][2 + pl], fb, sB + pl * kTileBh + j * kChunk, k0, n0 + 64 * j, bl);
                 } else {
 #pragma unroll
                   for (int j = 0; j < BN / 128; ++j)
@@ -718,21 +746,26 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
         const int bt = tile / tiles_per_img;
+        int tm, tn;
+        tile_coords(p, tile - bt * tiles_per_img, tm, tn);
+        const int m0 = tm * (2 * BM), n0 = tn * BN;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accumulate = 0;
         for (int t = 0; t < p.nterms; ++t) {
-          const int a_mn = p.a_mn[t], b_mn = p.b_mn[t];
-          const uint32_t idesc = ptx::idesc_bf16_f32(2 * BM, BN, a_mn, b_mn);
-          const uint32_t a_step = a_mn ? 2048u : 32u;
-          const uint32_t b_step = b_mn ? 2048u : 32u;
-          const uint32_t a_lbo = a_mn ? kChunk : 0u;
-          const uint32_t b_lbo = b_mn ? kChunk : 0u;
+          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
           const int nkb_all = (p.K[t] + BK - 1) / BK;
           const int kb_lo = p.splits > 1 ? (int)((long long)bt * nkb_all / p.splits) : 0;
           const int kb_hi = p.splits > 1 ? (int)((long long)(bt + 1) * nkb_all / p.splits) : nkb_all;
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            const int a_mn = a_sym ? sym_a_mn(m0, kb * BK) : p.a_mn[t];
+            const int b_mn = b_sym ? sym_b_mn(kb * BK, n0) : p.b_mn[t];
+            const uint32_t idesc = ptx::idesc_bf16_f32(2 * BM, BN, a_mn, b_mn);
+            const uint32_t a_step = a_mn ? 2048u : 32u;
+            const uint32_t b_step = b_mn ? 2048u : 32u;
+            const uint32_t a_lbo = a_mn ? kChunk : 0u;
+            const uint32_t b_lbo = b_mn ? kChunk : 0u;
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint32_t sA = smem_base + stage * C::kStageBytes;
@@ -785,7 +818,8 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
                                      m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
       if (p.dot_ws)
-        write_dot_partial(p, ds, lane, (long long)tile * (2 * kEpiWarps) + rank * kEpiWarps + (warp - 2));
+        write_dot_partial(p, (p.sym_out && (n0 >> 8) > (m0 >> 8)) ? 2.f * ds : ds, lane,
+                          (long long)tile * (2 * kEpiWarps) + rank * kEpiWarps + (warp - 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -987,7 +1021,12 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   p.tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   p.tiles_n = (g.N + BN - 1) / BN;
   p.tile_rows = ctas * BM;
-  p.triu_tiles = g.X.p0 ? 1 : 0;
+  p.triu_tiles = (g.X.p0 || g.sym_out) ? 1 : 0;
+  p.sym_out = g.sym_out ? 1 : 0;
+  if (g.sym_out && (g.M != g.N || g.split_k > 1)) {
+    set_error("gemm_tc: sym_out needs a square result and excludes split-K");
+    return cudaErrorInvalidValue;
+  }
   p.tiles_per_img = count_tiles(p.tiles_m, p.tiles_n, p.tile_rows, p.triu_tiles != 0);
   if (g.X.p0) {
     if (g.M != g.N || g.Cp.p0 || g.Cp2.p0 || g.split_k > 1 || g.dot_out) {
@@ -1003,14 +1042,20 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     p.K[t] = gt.K;
     p.a_mn[t] = gt.transA ? 1 : 0;   // stored [K,M]  -> M-major
     p.b_mn[t] = gt.transB ? 0 : 1;   // stored [K,N]  -> N-major ; [N,K] -> K-major
-    const int a_rows = gt.transA ? BK : BM;
-    const int b_rows = gt.transB ? BN / ctas : BK;
+    p.a_sym[t] = gt.symA ? 1 : 0;
+    p.b_sym[t] = gt.symB ? 1 : 0;
+    if ((gt.symA && g.M != gt.K) || (gt.symB && g.N != gt.K) || ((gt.symA || gt.symB) && g.split_k > 1)) {
+      set_error("gemm_tc: a symmetric operand must be square (M == K / N == K) and excludes split-K");
+      return cudaErrorInvalidValue;
+    }
+    const int a_rows = (gt.transA || gt.symA) ? BK : BM;
+    const int b_rows = gt.symB ? BK : (gt.transB ? BN / ctas : BK);
     // logical extents double as the TMA bounds: whatever lies outside reads as zero
     Mat A = gt.A, B = gt.B;
-    A.rows = gt.transA ? gt.K : g.M;
-    A.cols = gt.transA ? g.M : gt.K;
-    B.rows = gt.transB ? g.N : gt.K;
-    B.cols = gt.transB ? gt.K : g.N;
+    A.rows = (gt.transA && !gt.symA) ? gt.K : g.M;
+    A.cols = (gt.transA && !gt.symA) ? g.M : gt.K;
+    B.rows = (gt.transB && !gt.symB) ? g.N : gt.K;
+    B.cols = (gt.transB && !gt.symB) ? gt.K : g.N;
     const int ab_batch = g.split_k > 1 ? 1 : g.batch;
     if (!make_plane_map(&p.tm[t][0], A.p0, A, ab_batch, a_rows)) return cudaErrorInvalidValue;
     if (!make_plane_map(&p.tm[t][2], B.p0, B, ab_batch, b_rows)) return cudaErrorInvalidValue;

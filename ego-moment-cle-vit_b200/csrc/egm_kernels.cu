@@ -559,6 +559,53 @@ triu_unpack_planes_kernel(const float* __restrict__ dv, long long ld_dv, int d,
     if (threadIdx.x == 0) tr_partial[(long long)b * gridDim.x + blockIdx.x] = tr;
   }
 }
+// out = scale * s_b[b] * sym(unpack(dv[b])) with sym(X) = (X + X^T)/2, written in the symmetric
+// block storage of the GEMM engine: only 8-column groups inside the upper 256 x 256 blocks
+// (block column >= block row) are stored; the blocks below are never read by the engine.
+__global__ void __launch_bounds__(256)
+triu_unpack_sym_planes_kernel(const float* __restrict__ dv, long long ld_dv, int d,
+                              const float* __restrict__ s_b, float scale, WPtr out) {
+  const int b = blockIdx.y;
+  const int i0 = blockIdx.x * kUnpackRows;
+  const float sc = scale * (s_b ? s_b[b] : 1.f);
+  const int groups = (int)(out.ld / 8);
+  const float* src_b = dv + (long long)b * ld_dv;
+  for (int u = threadIdx.x; u < kUnpackRows * groups; u += blockDim.x) {
+    const int i = i0 + u / groups;
+    if (i >= d) break;
+    const int j0 = (u % groups) * 8;
+    if ((j0 >> 8) < (i >> 8)) continue;          // absent block
+    const float* src = src_b + (long long)i * d - (long long)i * (i - 1) / 2 - i;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q;
+      float x = 0.f;
+      if (j < d) {
+        if (j >= i) x = src[j];
+        else x = src_b[(long long)j * d - (long long)j * (j - 1) / 2 + (i - j)];   // mirror (diagonal blocks)
+      }
+      v[q] = (j == i ? sc : 0.5f * sc) * x;
+    }
+    const long long o = (long long)b * out.bs + (long long)i * out.ld + j0;
+    if (out.f) {
+      *reinterpret_cast<float4*>(out.f + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(out.f + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * q]), h1 = __float2bfloat16_rn(v[2 * q + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * q] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * q + 1] - __bfloat162float(h1));
+        hw[q] = __bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[q] = __bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(out.hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      if (out.lo) *reinterpret_cast<uint4*>(out.lo + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
 // fp32 matrix -> packed upper triangle as a working-matrix row (the Linear's operand)
 __global__ void __launch_bounds__(256)
 triu_pack_planes_kernel(const float* __restrict__ O, int d, WPtr out) {
@@ -1019,6 +1066,12 @@ void triu_unpack_planes(const float* dv, long long ld_dv, int batch, int d, cons
                         const W& out, float* tr_partial, int prec, cudaStream_t st) {
   dim3 grid(triu_unpack_blocks(d), batch);
   triu_unpack_planes_kernel<<<grid, 256, 0, st>>>(dv, ld_dv, d, s_b, wptr(out, prec), tr_partial);
+  note_launch();
+}
+void triu_unpack_sym_planes(const float* dv, long long ld_dv, int batch, int d, const float* s_b,
+                            float scale, const W& out, int prec, cudaStream_t st) {
+  dim3 grid(triu_unpack_blocks(d), batch);
+  triu_unpack_sym_planes_kernel<<<grid, 256, 0, st>>>(dv, ld_dv, d, s_b, scale, wptr(out, prec));
   note_launch();
 }
 void triu_pack_planes(const float* O, int batch, int d, const W& out, int prec, cudaStream_t st) {

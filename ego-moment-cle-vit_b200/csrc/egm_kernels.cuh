@@ -128,6 +128,10 @@ void colsum(const float* x, int m, int n, float* out, cudaStream_t st);   // out
 int triu_unpack_blocks(int d);
 void triu_unpack_planes(const float* dv, long long ld_dv, int batch, int d, const float* s_b,
                         const W& out, float* tr_partial, int prec, cudaStream_t st);
+// out = scale * s_b[b] * (unpack(dv[b]) + unpack(dv[b])^T)/2 in the GEMM engine's symmetric block
+// storage (upper 256 x 256 blocks only; see GemmTerm::symA)
+void triu_unpack_sym_planes(const float* dv, long long ld_dv, int batch, int d, const float* s_b,
+                            float scale, const W& out, int prec, cudaStream_t st);
 // out (a [batch, d(d+1)/2] working matrix with batch == 1 image of `batch` rows) = triu(O)
 void triu_pack_planes(const float* O, int batch, int d, const W& out, int prec, cudaStream_t st);
 // out[b] = sum_n dy[b,n] (y[b,n] - bias[n])

@@ -137,7 +137,8 @@ def gpf_fused_graph(tokens_anchor, tokens_positive, coef, *, cosine=True, eps=1e
         raise RuntimeError(f"token shapes differ: {tuple(a.shape)} vs {tuple(p.shape)}")
     if c.shape[0] > 16 or c.shape[1] > 16:
         raise RuntimeError("polynomial degrees above 15 are not supported")
-    return _GPFFunction.apply(a, p, c, cosine, eps, symmetric, _prec(precision))
+    G = _GPFFunction.apply(a, p, c, cosine, eps, symmetric, _prec(precision))
+    return mark_symmetric(G) if symmetric else G
 
 
 # -------------------------------------------------------------------------- pool
@@ -247,7 +248,7 @@ class _MomentHeadLinearFunction(Function):
     written by the last Newton-Schulz product straight into the Linear's operand planes."""
 
     @staticmethod
-    def forward(ctx, Z, G, weight, bias, iters, eps, want_u, lowrank, prec):
+    def forward(ctx, Z, G, weight, bias, iters, eps, want_u, lowrank, prec, flags):
         L = _lib.load()
         B, N, D = Z.shape
         n_out, K = weight.shape
@@ -270,7 +271,7 @@ class _MomentHeadLinearFunction(Function):
                 scal = torch.empty(3, B, device=dev, dtype=torch.float32)
                 state = _ws(L.egm_mhd_state_bytes(B, N, D, iters, prec), dev)
                 ws = _ws(L.egm_mhd_fwd_workspace(B, N, D, iters, prec), dev)
-                _lib.check(L.egm_mhd_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps),
+                _lib.check(L.egm_mhd_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps), int(flags),
                                          lin_state.data_ptr(), _p(u), vecs.data_ptr(), mu.data_ptr(),
                                          scal.data_ptr(), state.data_ptr(), prec, ws.data_ptr(), ws.numel(),
                                          _stream(dev)), "egm_mhd_fwd")
@@ -280,7 +281,8 @@ class _MomentHeadLinearFunction(Function):
                        "egm_linear_fwd")
         ctx.save_for_backward(Z, G, vecs, mu, scal, state, lin_state, y, *([bias] if bias is not None else []),
                               *([u] if want_u else []))
-        ctx.cfg = (int(iters), float(eps), bool(want_u), bool(lowrank), prec, bias is not None, n_out, K)
+        ctx.cfg = (int(iters), float(eps), bool(want_u), bool(lowrank), prec, bias is not None, n_out, K,
+                   int(flags))
         if want_u:
             return y, u
         return y
@@ -289,7 +291,7 @@ class _MomentHeadLinearFunction(Function):
     @once_differentiable
     def backward(ctx, dy, du=None):
         L = _lib.load()
-        iters, eps, want_u, lowrank, prec, has_bias, n_out, K = ctx.cfg
+        iters, eps, want_u, lowrank, prec, has_bias, n_out, K, flags = ctx.cfg
         saved = list(ctx.saved_tensors)
         Z, G, vecs, mu, scal, state, lin_state, y = saved[:8]
         rest = saved[8:]
@@ -327,9 +329,9 @@ class _MomentHeadLinearFunction(Function):
                 ws = _ws(L.egm_mhd_bwd_workspace(B, N, D, iters, prec), dev)
                 _lib.check(L.egm_mhd_bwd(dv.data_ptr(), dot.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), _p(u),
                                          vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
-                                         B, N, D, iters, eps, dZ.data_ptr(), dG.data_ptr(), prec,
+                                         B, N, D, iters, eps, flags, dZ.data_ptr(), dG.data_ptr(), prec,
                                          ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mhd_bwd")
-        return dZ, dG, dw, db, None, None, None, None, None
+        return dZ, dG, dw, db, None, None, None, None, None, None
 
 
 def moment_head_linear(tokens, graph, weight, bias, num_iterations, *, eps=1e-5, third_order=False,
@@ -354,7 +356,34 @@ def moment_head_linear(tokens, graph, weight, bias, num_iterations, *, eps=1e-5,
     if w.shape[1] != D * (D + 1) // 2:
         raise RuntimeError(f"linear: weight {tuple(w.shape)} does not match d_in={D}")
     b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
-    return _MomentHeadLinearFunction.apply(Z, G, w, b, int(num_iterations), eps, third_order, lowrank, prec)
+    flags = _lib.MHD_SYMMETRIC_GRAPH if (not lowrank and graph_is_symmetric(graph)) else 0
+    return _MomentHeadLinearFunction.apply(Z, G, w, b, int(num_iterations), eps, third_order, lowrank, prec,
+                                           flags)
+
+
+# ---- exact-symmetry tag of a graph tensor ---------------------------------------------------
+# GraphPolynomialFusion with symmetric_enforce emits G with G[i,j] == G[j,i] bit for bit
+# (0.5 * (F_ij + F_ji) in one kernel). The tag records the tensor's version counter, so an
+# in-place edit of G silently drops it; MomentHead then takes the general (any real matrix) path.
+_symmetric_fast_path = os.environ.get("EGM_SYMMETRIC_FAST_PATH", "1") != "0"
+
+
+def set_symmetric_fast_path(on: bool) -> None:
+    """Let MomentHead exploit a graph tagged exactly symmetric (default on): every Newton-Schulz
+    product then evaluates its upper tiles only and the backward runs as a symmetric tangent.
+    With the fast path the gradient returned for the graph is the reference's plus a skew-symmetric
+    matrix, which the symmetrisation inside GraphPolynomialFusion's backward removes."""
+    global _symmetric_fast_path
+    _symmetric_fast_path = bool(on)
+
+
+def mark_symmetric(graph: torch.Tensor) -> torch.Tensor:
+    graph._egm_symmetric_version = graph._version
+    return graph
+
+
+def graph_is_symmetric(graph: torch.Tensor) -> bool:
+    return _symmetric_fast_path and getattr(graph, "_egm_symmetric_version", None) == graph._version
 
 
 _ns_algorithm = os.environ.get("EGM_NS_ALGORITHM", "dense")

@@ -133,17 +133,25 @@ int egm_mlr_bwd(const float* dO, const float* dv, const float* dotOO, const floa
  * triangle of iSQRT-COV(M2) is written there, then egm_linear_fwd is called with x == NULL.
  * Backward: dv [B, D(D+1)/2] = gradient of the half-vector (egm_linear_bwd's dx), dotO [B] =
  * <dv_b, v_b> (for y = v W^T + b this equals <dy_b, y_b - b>: egm_rowdot_bias).
- * iters >= 2, tensor-core precision modes only. Saved: vecs, mu (as egm_pool_fwd), scal [3,B], state. */
+ * iters >= 2, tensor-core precision modes only. Saved: vecs, mu (as egm_pool_fwd), scal [3,B], state.
+ * flags: EGM_MHD_SYMMETRIC_GRAPH promises G == G^T exactly (the output of GraphPolynomialFusion with
+ * symmetric_enforce, gpf_kernel.py:150-152). Every matrix of the Newton-Schulz chain is then symmetric:
+ * only the upper 256 x 256 blocks of each product are evaluated and stored (6 of 9 tiles at D = 768),
+ * and the backward runs as a symmetric forward tangent (the Frechet derivative of a matrix polynomial
+ * at a symmetric point is self-adjoint). dZ is the same; dG differs from the general path by a
+ * skew-symmetric matrix, i.e. (dG + dG^T)/2 - all a symmetric-graph producer consumes - is the same.
+ * The same flags value must be passed to the matching backward. */
+enum { EGM_MHD_SYMMETRIC_GRAPH = 1 };
 size_t egm_mhd_state_bytes(int B, int N, int D, int iters, int prec);
 size_t egm_mhd_fwd_workspace(int B, int N, int D, int iters, int prec);
-int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps,
+int egm_mhd_fwd(const float* Z, const float* G, int B, int N, int D, int iters, float eps, int flags,
                 void* x_planes, float* u, float* vecs, float* mu, float* scal, void* state, int prec,
                 void* ws, size_t ws_bytes, egm_stream_t stream);
 size_t egm_mhd_bwd_workspace(int B, int N, int D, int iters, int prec);
 int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float* Z, const float* G,
                 const float* u, const float* vecs, const float* mu, const float* scal, const void* state,
-                int B, int N, int D, int iters, float eps, float* dZ, float* dG, int prec, void* ws,
-                size_t ws_bytes, egm_stream_t stream);
+                int B, int N, int D, int iters, float eps, int flags, float* dZ, float* dG, int prec,
+                void* ws, size_t ws_bytes, egm_stream_t stream);
 /* out[b] = sum_n dy[b,n] * (y[b,n] - bias[n])   (bias may be NULL) */
 int egm_rowdot_bias(const float* dy, const float* y, const float* bias, int B, int n, float* out,
                     egm_stream_t stream);

@@ -285,7 +285,117 @@ static int run_case(const Case& c) {
   return ok ? 0 : 1;
 }
 
-static void bench(int D, int batch, int npass, int tA, int tB) {
+
+// Symmetric block storage: operands are symmetric D x D matrices of which only the upper
+// 256 x 256 blocks are valid on the device (the absent blocks hold NaN); the product is
+// requested with sym_out, so only the upper blocks of C = S0 S1 (+ S2 S3) may be written.
+static int run_sym_case(const char* name, int D, int batch, int nterms, int npass, int with_e, int with_dot) {
+  HostMat S[4], E, F;
+  auto symmetrise = [&](HostMat& m, bool poison) {
+    for (int b = 0; b < m.batch; ++b)
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < i; ++j) m.f[(size_t)b * m.bs + (size_t)i * m.ld + j] = m.f[(size_t)b * m.bs + (size_t)j * m.ld + i];
+    for (size_t i = 0; i < m.f.size(); ++i) {
+      m.hi[i] = __float2bfloat16_rn(m.f[i]);
+      m.lo[i] = __float2bfloat16_rn(m.f[i] - __bfloat162float(m.hi[i]));
+    }
+    std::vector<__nv_bfloat16> dh = m.hi, dl = m.lo;
+    if (poison)
+      for (int b = 0; b < m.batch; ++b)
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j)
+            if ((j >> 8) < (i >> 8)) {
+              dh[(size_t)b * m.bs + (size_t)i * m.ld + j] = __ushort_as_bfloat16(0x7FC0);
+              dl[(size_t)b * m.bs + (size_t)i * m.ld + j] = __ushort_as_bfloat16(0x7FC0);
+            }
+    CK(cudaMemcpy(m.d_hi, dh.data(), dh.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.d_lo, dl.data(), dl.size() * 2, cudaMemcpyHostToDevice));
+  };
+  GemmProblem g;
+  g.M = D; g.N = D; g.batch = batch; g.nterms = nterms; g.sym_out = 1;
+  for (int t = 0; t < 2 * nterms; ++t) { S[t].init(D, D, batch, 0, true); symmetrise(S[t], true); }
+  for (int t = 0; t < nterms; ++t) {
+    g.t[t].A = S[2 * t].planes(); g.t[t].symA = 1;
+    g.t[t].B = S[2 * t + 1].planes(); g.t[t].symB = 1;
+    if (npass != 3) { g.t[t].A.p1 = nullptr; g.t[t].B.p1 = nullptr; }
+    g.t[t].K = D;
+  }
+  g.alpha = -0.5f; g.beta_eye = 1.5f;
+  if (with_e) {
+    E.init(D, D, batch, 0, true); symmetrise(E, true);
+    g.E = E.planes(); g.e_planes = 1; g.gamma = -3.f;
+    if (npass != 3) g.E.p1 = nullptr;
+  }
+  const long long ldp = ((D + 7) / 8) * 8, bsp = (long long)D * ldp;
+  __nv_bfloat16 *d_ch, *d_cl;
+  CK(cudaMalloc(&d_ch, bsp * batch * 2)); CK(cudaMalloc(&d_cl, bsp * batch * 2));
+  CK(cudaMemset(d_ch, 0xFF, bsp * batch * 2)); CK(cudaMemset(d_cl, 0xFF, bsp * batch * 2));
+  g.Cp.p0 = d_ch; g.Cp.p1 = npass == 3 ? d_cl : nullptr; g.Cp.rows = D; g.Cp.cols = D; g.Cp.ld = ldp; g.Cp.bstride = bsp;
+  float *d_dot = nullptr, *d_dotws = nullptr;
+  if (with_dot) {
+    F.init(D, D, batch, 0, true); symmetrise(F, true);
+    g.F = F.planes(); g.f_planes = 1;
+    if (npass != 3) g.F.p1 = nullptr;
+    CK(cudaMalloc(&d_dot, batch * 4));
+    g.dot_out = d_dot;
+    CK(cudaMalloc(&d_dotws, egm::gemm_tc_dot_ws_floats(g) * 4 + 16));
+    g.dot_ws = d_dotws;
+  }
+  cudaError_t le = egm::gemm_tc(g, npass, 0);
+  if (le != cudaSuccess) {
+    printf("[FAIL] %-44s launch: %s (%s)\n", name, cudaGetErrorString(le), egm::last_error());
+    return 1;
+  }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("[FAIL] %-44s kernel: %s\n", name, cudaGetErrorString(se)); exit(3); }
+  std::vector<__nv_bfloat16> ch(bsp * batch), cl(bsp * batch);
+  CK(cudaMemcpy(ch.data(), d_ch, ch.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cl.data(), d_cl, cl.size() * 2, cudaMemcpyDeviceToHost));
+  std::vector<float> dots(batch, 0.f);
+  if (with_dot) CK(cudaMemcpy(dots.data(), d_dot, batch * 4, cudaMemcpyDeviceToHost));
+  double max_ref = 0, max_err = 0, max_err_dot = 0;
+  bool untouched = true;
+  for (int b = 0; b < batch; ++b) {
+    double dref = 0, dabs = 0;
+    for (int m = 0; m < D; ++m)
+      for (int n = 0; n < D; ++n) {
+        const size_t o = (size_t)b * bsp + (size_t)m * ldp + n;
+        if ((n >> 8) < (m >> 8)) {   // absent block: must not have been written
+          if (__bfloat16_as_ushort(ch[o]) != 0xFFFF) untouched = false;
+          continue;
+        }
+        double acc = 0;
+        for (int t = 0; t < nterms; ++t)
+          for (int k = 0; k < D; ++k) acc += S[2 * t].val(b, m, k, npass) * S[2 * t + 1].val(b, k, n, npass);
+        double ref = -0.5 * acc + (m == n ? 1.5 : 0.0);
+        if (with_e) ref += -3.0 * E.val(b, m, n, npass);
+        if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        double got = __bfloat162float(ch[o]);
+        if (npass == 3) got += __bfloat162float(cl[o]);
+        if (!(fabs(got - ref) <= max_err)) max_err = fabs(got - ref);
+        if (with_dot) {
+          const double w = ((n >> 8) > (m >> 8)) ? 2.0 : 1.0;
+          dref += w * ref * F.val(b, m, n, npass); dabs += fabs(w * ref * F.val(b, m, n, npass));
+        }
+      }
+    if (with_dot) { const double e = fabs(dots[b] - dref) / (dabs + 1e-30); if (!(e <= max_err_dot)) max_err_dot = e; }
+  }
+  const double tol = (npass == 3) ? 8e-5 : 6e-3;
+  const double r = max_err / (max_ref + 1e-30);
+  const bool ok = r < tol && untouched && max_ref > 0 && (!with_dot || max_err_dot < 2e-5);
+  printf("[%s] %-44s rel_err planes=%.2e (max|ref|=%.3g)%s", ok ? " ok " : "FAIL", name, r, max_ref,
+         untouched ? "" : " LOWER-BLOCK-WRITTEN");
+  if (with_dot) printf(" dot=%.2e", max_err_dot);
+  printf("\n");
+  fflush(stdout);
+  for (int t = 0; t < 2 * nterms; ++t) S[t].free_();
+  if (with_e) E.free_();
+  if (with_dot) F.free_();
+  cudaFree(d_ch); cudaFree(d_cl); cudaFree(d_dot); cudaFree(d_dotws);
+  return ok ? 0 : 1;
+}
+
+static void bench(int D, int batch, int npass, int tA, int tB, int sym = 0, int nterms = 1) {
   HostMat A, B;
   A.init(D, D, 1, 0, true); B.init(D, D, 1, 0, true);
   // replicate one image `batch` times on the device
@@ -305,6 +415,8 @@ static void bench(int D, int batch, int npass, int tA, int tB) {
   g.t[0].A.p0 = ah; g.t[0].A.p1 = al; g.t[0].A.rows = D; g.t[0].A.cols = D; g.t[0].A.ld = D; g.t[0].A.bstride = per;
   g.t[0].B = g.t[0].A; g.t[0].B.p0 = bh; g.t[0].B.p1 = bl;
   g.t[0].transA = tA; g.t[0].transB = tB; g.t[0].K = D;
+  if (sym) { g.t[0].symA = g.t[0].symB = 1; g.sym_out = 1; }
+  if (nterms == 2) { g.nterms = 2; g.t[1] = g.t[0]; }
   g.alpha = -0.5f; g.beta_eye = 1.5f;
   g.Cp.p0 = ch; g.Cp.p1 = npass == 3 ? cl : nullptr; g.Cp.rows = D; g.Cp.cols = D; g.Cp.ld = D; g.Cp.bstride = per;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -316,9 +428,13 @@ static void bench(int D, int batch, int npass, int tA, int tB) {
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
-  double flops = 2.0 * D * D * D * batch;
-  printf("[perf] D=%d batch=%d npass=%d tA=%d tB=%d : %.3f ms  %.1f TFLOP/s algorithmic (%.1f executed)\n",
-         D, batch, npass, tA, tB, ms, flops / ms * 1e-9, flops * npass / ms * 1e-9);
+  double flops = 2.0 * D * D * D * batch * nterms;
+  if (sym) {   // only the upper 256-block tiles are evaluated
+    const int nb = (D + 255) / 256;
+    flops *= (double)(nb * (nb + 1) / 2) / (nb * nb);
+  }
+  printf("[perf] D=%d batch=%d npass=%d tA=%d tB=%d sym=%d terms=%d : %.3f ms  %.1f TFLOP/s evaluated (%.1f executed)\n",
+         D, batch, npass, tA, tB, sym, nterms, ms, flops / ms * 1e-9, flops * npass / ms * 1e-9);
   fflush(stdout);
   cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl); cudaFree(ch); cudaFree(cl);
   A.free_(); B.free_();
@@ -398,7 +514,18 @@ int main(int argc, char** argv) {
   };
   const int ncases = sizeof(cases) / sizeof(cases[0]);
   for (int i = 0; i < ncases; ++i) fails += run_case(cases[i]);
+  fails += run_sym_case("sym 768 b2 x3 1 term", 768, 2, 1, 3, 0, 0);
+  fails += run_sym_case("sym 768 b2 x3 2 terms + E + dot", 768, 2, 2, 3, 1, 1);
+  fails += run_sym_case("sym 768 b2 x1 2 terms + dot", 768, 2, 2, 1, 0, 1);
+  fails += run_sym_case("sym 1024 b1 x3 1 term + E", 1024, 1, 1, 3, 1, 0);
+  fails += run_sym_case("sym 600 b2 x3 ragged 2 terms + dot", 600, 2, 2, 3, 0, 1);
+  fails += run_sym_case("sym 200 b3 x3 single block", 200, 3, 1, 3, 1, 1);
   if (!quick) {
+    bench(768, 256, 3, 0, 0, 1, 1);
+    bench(768, 256, 3, 0, 0, 1, 2);
+    bench(768, 256, 1, 0, 0, 1, 1);
+    bench(768, 256, 1, 0, 0, 1, 2);
+    bench(768, 256, 3, 0, 0, 0, 2);
     bench(768, 64, 1, 0, 0);
     bench(768, 64, 3, 0, 0);
     bench(768, 256, 1, 0, 0);

@@ -202,6 +202,97 @@ def test_fused_moment_head_linear_matches_the_oracle(pkg, dev, algo, K, shape):
         assert EF.moment_head_linear(Z.to(dev), graph.to(dev), Wt.to(dev), None, K) is None
 
 
+@pytest.mark.parametrize("K", [2, 3, 5])
+@pytest.mark.parametrize("shape", [(3, 21, 40), (2, 50, 136), (2, 70, 300), (1, 40, 520)])
+def test_symmetric_graph_fast_path_matches_the_oracle(pkg, dev, K, shape):
+    """EGM_MHD_SYMMETRIC_GRAPH: with an exactly symmetric graph every Newton-Schulz matrix is symmetric;
+    the engine evaluates / stores upper 256-blocks only and the backward is the symmetric tangent chain.
+    y, u, dZ, dW, db equal the oracle; dG equals the oracle's up to a skew-symmetric part."""
+    EF = pkg.functional
+    B, N, D = shape
+    g = torch.Generator().manual_seed(11 * K + D)
+    Z = torch.randn(B, N, D, generator=g)
+    graph = torch.rand(B, N, N, generator=g) + 0.05
+    graph = 0.5 * (graph + graph.transpose(-2, -1))          # exactly symmetric in fp32
+    assert torch.equal(graph, graph.transpose(-2, -1))
+    L, n_out = D * (D + 1) // 2, 16
+    Wt = torch.randn(n_out, L, generator=g) / L ** 0.5
+    bias = torch.randn(n_out, generator=g)
+    dy = torch.randn(B, n_out, generator=g)
+    du = torch.randn(B, D, generator=g)
+    st = O.moment_forward(npy(Z), npy(graph), K, 1e-5, {"hashes": np.zeros((3, D), np.int64),
+                                                        "signs": np.ones((3, D), np.int64), "sketch_dim": 4})
+    y_ref = st["vec"] @ npy(Wt).T + npy(bias)
+    dZ, dG = O.moment_backward(npy(Z), npy(graph), K, npy(dy) @ npy(Wt), 1e-5, None, None, du=npy(du))
+    sym = lambda x: 0.5 * (x + np.swapaxes(x, -1, -2))
+    for mode, tol in (("fp32", 1e-3), ("bf16", 6e-2)):
+        with EF.precision(mode):
+            z = Z.to(dev).requires_grad_(True)
+            gr = EF.mark_symmetric(graph.to(dev).requires_grad_(True))
+            assert EF.graph_is_symmetric(gr)
+            w = Wt.to(dev).requires_grad_(True)
+            b = bias.to(dev).requires_grad_(True)
+            y, u = EF.moment_head_linear(z, gr, w, b, K, eps=1e-5, third_order=True, algorithm="dense")
+            ((y * dy.to(dev)).sum() + (u * du.to(dev)).sum()).backward()
+        assert rel_err(npy(y), y_ref) < tol
+        assert rel_err(npy(u), st["u"]) < tol
+        assert rel_err(npy(z.grad), dZ) < 3 * tol
+        assert rel_err(sym(npy(gr.grad)), sym(dG)) < 3 * tol
+        assert rel_err(npy(w.grad), npy(dy).T @ st["vec"]) < tol
+        assert rel_err(npy(b.grad), npy(dy).sum(0)) < 1e-5
+
+
+def test_symmetric_tag_follows_the_tensor_version(pkg, dev):
+    """GraphPolynomialFusion tags its (bit-exactly symmetric) output; an in-place edit or
+    symmetric_enforce=False drops the tag, and the switch turns the fast path off."""
+    EF = pkg.functional
+    a, p = (t.to(dev) for t in make_inputs(2, 30, 64))
+    gpf = pkg.GraphPolynomialFusion(2, 2).to(dev)
+    G = gpf(a, p)
+    assert torch.equal(G, G.transpose(-2, -1)) and EF.graph_is_symmetric(G)
+    EF.set_symmetric_fast_path(False)
+    try:
+        assert not EF.graph_is_symmetric(G)
+    finally:
+        EF.set_symmetric_fast_path(True)
+    with torch.no_grad():
+        G[:, 0, 1] += 1.0
+    assert not EF.graph_is_symmetric(G)
+    assert not EF.graph_is_symmetric(pkg.GraphPolynomialFusion(2, 2, symmetric_enforce=False).to(dev)(a, p))
+    assert not EF.graph_is_symmetric(gpf(a, p).detach().clone())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_fast_path_and_general_path_give_the_same_training_gradients(pkg, dev, mode):
+    """GPF -> MomentHead (BASELINE config 1 shape, B=4): outputs and every gradient the optimiser sees
+    agree between the symmetric fast path and the general chain."""
+    EF = pkg.functional
+    B, N, D = 4, 197, 768
+    a0, p0 = make_inputs(B, N, D)
+    torch.manual_seed(0)
+    gpf = pkg.GraphPolynomialFusion(3, 3).to(dev)
+    head = pkg.MomentHead(D, 256, isqrt_iterations=5).to(dev).eval()
+    dout = torch.randn(B, 256, generator=torch.Generator().manual_seed(4321)).to(dev)
+    res = {}
+    for fast in (True, False):
+        EF.set_symmetric_fast_path(fast)
+        try:
+            with EF.precision(mode):
+                a = a0.to(dev).requires_grad_(True)
+                p = p0.to(dev).requires_grad_(True)
+                gpf.zero_grad(); head.zero_grad()
+                out = head(a, gpf(a, p))
+                (out * dout).sum().backward()
+        finally:
+            EF.set_symmetric_fast_path(True)
+        res[fast] = [npy(out), npy(a.grad), npy(p.grad), npy(gpf.alpha_coeffs.grad),
+                     npy(head.second_net[0].weight.grad)]
+    # each path sits within ~5e-4 (fp32 mode) of the fp64 oracle on token gradients (tests/gpu_fused_report.py)
+    tol = 1e-3 if mode == "fp32" else 6e-2
+    for x, y in zip(res[True], res[False]):
+        assert rel_err(x, y) < tol
+
+
 # ----------------------------------------------------------- golden fixtures (reference)
 def _build_from_golden(pkg, rec, dev):
     B, N, D, P, Q, K, d_out, third, S, sym, train = [int(v) for v in rec["cfg"]]
