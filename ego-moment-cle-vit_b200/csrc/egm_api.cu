@@ -277,8 +277,8 @@ int pool_bwd_tail(const W& Wn, const W& Zc, const W& V1, const W& V2, const floa
   }
   k::pool_bwd_dmu(dZc, du, sw, t, B, N, D, eps, dmu, st);
   k::pool_bwd_rows(dZc, Z, Zc, w, t, mu, u, du, dmu, B, N, D, eps, dZ, dw, dt, prec, st);
-  k::pool_bwd_ds(dW, ldW, dw, dt, G, s, B, N, ds, st);
-  k::pool_bwd_dG(dW, ldW, dw, dt, s, deg, ds, B, N, eps, dG, st);
+  k::pool_bwd_ds(dW, ldW, dw, dt, G, s, B, N, sym ? 1 : 0, ds, st);
+  k::pool_bwd_dG(dW, ldW, dw, dt, s, deg, ds, B, N, eps, sym ? 1 : 0, dG, st);
   EGM_LAUNCHED();
   return EGM_OK;
 }
@@ -728,8 +728,8 @@ int egm_mhd_bwd(const float* dv, const float* dotO, const float* du, const float
   fin.dot_ws = dot_ws;
   if (sym) {
     // symmetric graph: sym(dA) by the tangent chain (upper tiles only), then dM = inv dA + dtau I is
-    // symmetric, V1 == V2, and the dG returned is the reference's plus a skew-symmetric matrix -
-    // which every symmetric-graph producer (GraphPolynomialFusion's symmetrisation) annihilates
+    // symmetric, V1 == V2, and the dG returned is the symmetric part of the reference's - the only
+    // part a symmetric-graph producer (GraphPolynomialFusion's symmetrisation) lets through
     k::triu_unpack_sym_planes(dv, L, B, D, post, -0.5f, buf[0], prec, st);   // Y'_1 = -post sym(dO)/2
     EGM_LAUNCHED();
     const int rc = ns_tangent_bwd(S, prec, buf, fin, st);

@@ -219,32 +219,72 @@ __device__ __forceinline__ float poly_eval(const float (&pa)[MD + 1], const floa
   return f;
 }
 
-template <int MD>
-__global__ void gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
-                                    long long ldR, const float* __restrict__ coef, int P, int Q,
-                                    int symmetric, int n, float* __restrict__ G) {
-  __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
-  for (int t = threadIdx.x; t < (P + 1) * (Q + 1); t += blockDim.x) c[t] = coef[t];
-  __syncthreads();
-  const int b = blockIdx.z, i = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const long long base = (long long)b * n * ldR;
-  float pa[MD + 1], pb[MD + 1];
-  had_powers<MD>(Ra[base + (long long)i * ldR + j], P, pa);
-  had_powers<MD>(Rp[base + (long long)i * ldR + j], Q, pb);
-  float f = poly_eval<MD>(pa, pb, c, P, Q);
-  if (symmetric) {
-    had_powers<MD>(Ra[base + (long long)j * ldR + i], P, pa);
-    had_powers<MD>(Rp[base + (long long)j * ldR + i], Q, pb);
-    const float ft = poly_eval<MD>(pa, pb, c, P, Q);
-    f = 0.5f * (f + ft);
-  }
-  G[((long long)b * n + i) * n + j] = fmaxf(f, 0.f);
+// The polynomial kernels work on PAIRS of 32 x 32 tiles, (ti,tj) and its mirror (tj,ti), ti <= tj:
+// the mirror tile is staged in shared memory with coalesced loads and read transposed, so a thread
+// owns the element pair (i,j)/(j,i), evaluates it once, writes (i,j) directly and hands (j,i) back
+// through shared memory for a coalesced store. No strided global access anywhere.
+constexpr int kPT = 32;
+__host__ __device__ inline int poly_tiles(int n) { return (n + kPT - 1) / kPT; }
+__host__ __device__ inline int poly_pairs(int n) { return poly_tiles(n) * (poly_tiles(n) + 1) / 2; }
+__device__ __forceinline__ void poly_pair_coords(int pair, int nt, int& ti, int& tj) {
+  ti = 0;
+  while (pair >= nt - ti) { pair -= nt - ti; ++ti; }
+  tj = ti + pair;
 }
 
-// one block handles a strip of rows of one image; deterministic two-stage dcoef reduction
-constexpr int kPolyBwdRows = 8;
+template <int MD>
+__global__ void __launch_bounds__(256)
+gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp, long long ldR,
+                    const float* __restrict__ coef, int P, int Q, int symmetric, int n,
+                    float* __restrict__ G) {
+  __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
+  __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1];
+  for (int t = threadIdx.x; t < (P + 1) * (Q + 1); t += blockDim.x) c[t] = coef[t];
+  const int b = blockIdx.y;
+  int ti, tj;
+  poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long rb = (long long)b * n * ldR;
+  const long long gb = (long long)b * n * n;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // mirror tile (tj, ti)
+    const int r = ty + 8 * k, i2 = tj * kPT + r, j2 = ti * kPT + tx;
+    const bool ok = i2 < n && j2 < n;
+    sa[r][tx] = ok ? Ra[rb + (long long)i2 * ldR + j2] : 0.f;
+    sp[r][tx] = ok ? Rp[rb + (long long)i2 * ldR + j2] : 0.f;
+  }
+  __syncthreads();
+  float g2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k, i = ti * kPT + r, j = tj * kPT + tx;
+    g2[k] = 0.f;
+    if (i < n && j < n) {
+      float pa[MD + 1], pb[MD + 1];
+      had_powers<MD>(Ra[rb + (long long)i * ldR + j], P, pa);
+      had_powers<MD>(Rp[rb + (long long)i * ldR + j], Q, pb);
+      const float f = poly_eval<MD>(pa, pb, c, P, Q);
+      had_powers<MD>(sa[tx][r], P, pa);
+      had_powers<MD>(sp[tx][r], Q, pb);
+      const float ft = poly_eval<MD>(pa, pb, c, P, Q);
+      const float g1 = fmaxf(symmetric ? 0.5f * (f + ft) : f, 0.f);
+      g2[k] = symmetric ? g1 : fmaxf(ft, 0.f);
+      G[gb + (long long)i * n + j] = g1;
+    }
+  }
+  if (ti == tj) return;   // block-uniform: a diagonal tile is its own mirror
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sa[tx][ty + 8 * k] = g2[k];   // element (j,i): mirror-tile row tx, column r
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k, i2 = tj * kPT + r, j2 = ti * kPT + tx;
+    if (i2 < n && j2 < n) G[gb + (long long)i2 * n + j2] = sa[r][tx];
+  }
+}
+
+// one block per tile pair of one image; deterministic two-stage dcoef reduction
 template <int MD>
 __global__ void __launch_bounds__(256)
 gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
@@ -253,70 +293,110 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
                     float* __restrict__ partial) {
   __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
   __shared__ float red[(kMaxDeg + 1) * (kMaxDeg + 1)];
-  __shared__ float sh[32];
-  const int nt = (P + 1) * (Q + 1);
-  for (int t = threadIdx.x; t < nt; t += blockDim.x) { c[t] = coef[t]; red[t] = 0.f; }
-  __syncthreads();
+  __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1], sg[kPT][kPT + 1];
+  __shared__ float wacc[8][16];
+  const int nterm = (P + 1) * (Q + 1);
+  for (int t = threadIdx.x; t < nterm; t += blockDim.x) { c[t] = coef[t]; red[t] = 0.f; }
   const int b = blockIdx.y;
-  const int i0 = blockIdx.x * kPolyBwdRows;
+  int ti, tj;
+  poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  const bool offdiag = ti != tj;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long rb = (long long)b * n * ldR;
   const long long gb = (long long)b * n * n;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // mirror tile (tj, ti)
+    const int r = ty + 8 * k, i2 = tj * kPT + r, j2 = ti * kPT + tx;
+    const bool ok = i2 < n && j2 < n;
+    sa[r][tx] = ok ? Ra[rb + (long long)i2 * ldR + j2] : 0.f;
+    sp[r][tx] = ok ? Rp[rb + (long long)i2 * ldR + j2] : 0.f;
+    sg[r][tx] = ok ? dG[gb + (long long)i2 * n + j2] : 0.f;
+  }
+  __syncthreads();
   // small-degree fast path keeps the per-term sums in registers
   float acc[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) acc[t] = 0.f;
-  for (int e = threadIdx.x; e < kPolyBwdRows * n; e += blockDim.x) {
-    const int i = i0 + e / n, j = e % n;
-    if (i >= n) break;
-    float pa[MD + 1], pb[MD + 1], pat[MD + 1], pbt[MD + 1];
-    const float ra = Ra[rb + (long long)i * ldR + j], rp = Rp[rb + (long long)i * ldR + j];
-    const float rat = Ra[rb + (long long)j * ldR + i], rpt = Rp[rb + (long long)j * ldR + i];
-    had_powers<MD>(ra, P, pa); had_powers<MD>(rp, Q, pb);
-    had_powers<MD>(rat, P, pat); had_powers<MD>(rpt, Q, pbt);
-    const float f = poly_eval<MD>(pa, pb, c, P, Q), ft = poly_eval<MD>(pat, pbt, c, P, Q);
-    const float g_ij = dG[gb + (long long)i * n + j], g_ji = dG[gb + (long long)j * n + i];
-    float dF_ij, dF_ji;
-    if (symmetric) {
-      const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
-      dF_ij = dF_ji = 0.5f * (g_ij + g_ji) * sgate;
-    } else {
-      dF_ij = (f >= 0.f) ? g_ij : 0.f;
-      dF_ji = (ft >= 0.f) ? g_ji : 0.f;
-    }
-    // dRa_ij + dRa_ji  and  dRp_ij + dRp_ji
-    float da[MD + 1], db[MD + 1], dat[MD + 1], dbt[MD + 1];
-    had_dpowers<MD>(ra, P, da); had_dpowers<MD>(rp, Q, db);
-    had_dpowers<MD>(rat, P, dat); had_dpowers<MD>(rpt, Q, dbt);
-    const float ea = dF_ij * poly_eval<MD>(da, pb, c, P, Q) + dF_ji * poly_eval<MD>(dat, pbt, c, P, Q);
-    const float ep = dF_ij * poly_eval<MD>(pa, db, c, P, Q) + dF_ji * poly_eval<MD>(pat, dbt, c, P, Q);
-    wstore(Ea, (long long)b * Ea.bs + (long long)i * Ea.ld + j, ea);
-    wstore(Ep, (long long)b * Ep.bs + (long long)i * Ep.ld + j, ep);
-    if (MD == 3) {
-      // acc[4p+q]: static register indices; re-packed to the (Q+1)-strided order on output
+  float ea_k[4], ep_k[4];
 #pragma unroll
-      for (int pp = 0; pp < 4; ++pp)
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k, i = ti * kPT + r, j = tj * kPT + tx;
+    ea_k[k] = ep_k[k] = 0.f;
+    if (i < n && j < n) {
+      float pa[MD + 1], pb[MD + 1], pat[MD + 1], pbt[MD + 1];
+      const float ra = Ra[rb + (long long)i * ldR + j], rp = Rp[rb + (long long)i * ldR + j];
+      const float rat = sa[tx][r], rpt = sp[tx][r];
+      had_powers<MD>(ra, P, pa); had_powers<MD>(rp, Q, pb);
+      had_powers<MD>(rat, P, pat); had_powers<MD>(rpt, Q, pbt);
+      const float f = poly_eval<MD>(pa, pb, c, P, Q), ft = poly_eval<MD>(pat, pbt, c, P, Q);
+      const float g_ij = dG[gb + (long long)i * n + j], g_ji = sg[tx][r];
+      float dF_ij, dF_ji;
+      if (symmetric) {
+        const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
+        dF_ij = dF_ji = 0.5f * (g_ij + g_ji) * sgate;
+      } else {
+        dF_ij = (f >= 0.f) ? g_ij : 0.f;
+        dF_ji = (ft >= 0.f) ? g_ji : 0.f;
+      }
+      // E = dR + dR^T is symmetric: the same value goes to (i,j) and (j,i)
+      float da[MD + 1], db[MD + 1], dat[MD + 1], dbt[MD + 1];
+      had_dpowers<MD>(ra, P, da); had_dpowers<MD>(rp, Q, db);
+      had_dpowers<MD>(rat, P, dat); had_dpowers<MD>(rpt, Q, dbt);
+      const float ea = dF_ij * poly_eval<MD>(da, pb, c, P, Q) + dF_ji * poly_eval<MD>(dat, pbt, c, P, Q);
+      const float ep = dF_ij * poly_eval<MD>(pa, db, c, P, Q) + dF_ji * poly_eval<MD>(pat, dbt, c, P, Q);
+      ea_k[k] = ea; ep_k[k] = ep;
+      wstore(Ea, (long long)b * Ea.bs + (long long)i * Ea.ld + j, ea);
+      wstore(Ep, (long long)b * Ep.bs + (long long)i * Ep.ld + j, ep);
+      // dcoef: this thread's (i,j) term, plus the (j,i) term when the mirror tile is not this tile
+      const float dF_m = offdiag ? dF_ji : 0.f;
+      if (MD == 3) {
+        // acc[4p+q]: static register indices; re-packed to the (Q+1)-strided order on output
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq)
-          acc[pp * 4 + qq] = fmaf(dF_ij, pa[pp < MD + 1 ? pp : 0] * pb[qq < MD + 1 ? qq : 0], acc[pp * 4 + qq]);
-    } else {
-      for (int pp = 0; pp <= P; ++pp)
-        for (int qq = 0; qq <= Q; ++qq) atomicAdd(&red[pp * (Q + 1) + qq], dF_ij * pa[pp] * pb[qq]);
+        for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            acc[pp * 4 + qq] += dF_ij * (pa[pp] * pb[qq]) + dF_m * (pat[pp] * pbt[qq]);
+      } else {
+        for (int pp = 0; pp <= P; ++pp)
+          for (int qq = 0; qq <= Q; ++qq)
+            atomicAdd(&red[pp * (Q + 1) + qq], dF_ij * pa[pp] * pb[qq] + dF_m * pat[pp] * pbt[qq]);
+      }
     }
   }
-  float* out = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * nt;
+  if (offdiag) {   // block-uniform
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sa[tx][ty + 8 * k] = ea_k[k]; sp[tx][ty + 8 * k] = ep_k[k]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = ty + 8 * k, i2 = tj * kPT + r, j2 = ti * kPT + tx;
+      if (i2 < n && j2 < n) {
+        wstore(Ea, (long long)b * Ea.bs + (long long)i2 * Ea.ld + j2, sa[r][tx]);
+        wstore(Ep, (long long)b * Ep.bs + (long long)i2 * Ep.ld + j2, sp[r][tx]);
+      }
+    }
+  }
+  float* out = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * nterm;
   if (MD == 3) {
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp)
+    for (int t = 0; t < 16; ++t) {
+      const float v = warp_sum(acc[t]);
+      if (tx == 0) wacc[ty][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int pp = threadIdx.x >> 2, qq = threadIdx.x & 3;
+      if (pp <= P && qq <= Q) {
+        float v = 0.f;
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        if (pp <= P && qq <= Q) {   // block-uniform
-          const float v = block_sum(acc[pp * 4 + qq], sh);
-          if (threadIdx.x == 0) out[pp * (Q + 1) + qq] = v;
-        }
+        for (int w = 0; w < 8; ++w) v += wacc[w][threadIdx.x];
+        out[pp * (Q + 1) + qq] = v;
       }
+    }
   } else {
     __syncthreads();
-    for (int t = threadIdx.x; t < nt; t += blockDim.x) out[t] = red[t];
+    for (int t = threadIdx.x; t < nterm; t += blockDim.x) out[t] = red[t];
   }
 }
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int nt,
@@ -367,12 +447,18 @@ __global__ void weight_kernel(const float* __restrict__ G, const float* __restri
 }
 
 // ------------------------------------------------------------- mean / centre
-__global__ void __launch_bounds__(128)
+// Block = 64 columns x 8 row groups (512 threads): row group g walks rows g, g+8, ...; the weighted
+// column sums are combined through shared memory, then every group centres and stores its own rows
+// (second read of the block's 64-column slab hits L2). 8x the loads in flight of a thread-per-column
+// layout, which is what an HBM-bound pass over a [197 x 768] image needs.
+constexpr int kMcCols = 64, kMcGroups = 8;
+__global__ void __launch_bounds__(kMcCols * kMcGroups)
 mean_center_kernel(const float* __restrict__ Z, const float* __restrict__ w,
                    const float* __restrict__ wdiag, int n, int d, float eps, float* __restrict__ t_out,
                    float* __restrict__ sw_out, float* __restrict__ mu, float* __restrict__ u, WPtr Zc) {
   extern __shared__ float shw[];  // n weights
   __shared__ float sh[32];
+  __shared__ float part[kMcGroups][kMcCols];
   const int b = blockIdx.y;
   float tl = 0.f, sl = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -384,22 +470,41 @@ mean_center_kernel(const float* __restrict__ Z, const float* __restrict__ w,
   const float t = block_sum(tl, sh);
   const float sw = block_sum(sl, sh);
   if (blockIdx.x == 0 && threadIdx.x == 0) { t_out[b] = t; sw_out[b] = sw; }
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d) return;
+  const int tx = threadIdx.x % kMcCols, g = threadIdx.x / kMcCols;
+  const int j = blockIdx.x * kMcCols + tx;
+  const bool ok = j < d;
   const float* z = Z + (long long)b * n * d + j;
   float a = 0.f;
-  for (int i = 0; i < n; ++i) a = fmaf(shw[i], z[(long long)i * d], a);
+  if (ok)
+    for (int i = g; i < n; i += kMcGroups) a = fmaf(shw[i], z[(long long)i * d], a);
+  part[g][tx] = a;
+  __syncthreads();
+  a = 0.f;
+#pragma unroll
+  for (int q = 0; q < kMcGroups; ++q) a += part[q][tx];   // same order in every group: one value of mu
+  __syncthreads();
   const float inv = 1.f / (t + eps);
   const float m = a * inv;
-  mu[(long long)b * d + j] = m;
   float ua = 0.f;
-  const long long o = (long long)b * Zc.bs + j;
-  for (int i = 0; i < n; ++i) {
-    const float zc = z[(long long)i * d] - m;
-    ua = fmaf(zc, shw[i], ua);
-    wstore(Zc, o + (long long)i * Zc.ld, zc);
+  if (ok) {
+    if (g == 0) mu[(long long)b * d + j] = m;
+    const long long o = (long long)b * Zc.bs + j;
+    for (int i = g; i < n; i += kMcGroups) {
+      const float zc = z[(long long)i * d] - m;
+      ua = fmaf(zc, shw[i], ua);
+      wstore(Zc, o + (long long)i * Zc.ld, zc);
+    }
   }
-  if (u) u[(long long)b * d + j] = ua * inv;
+  if (u) {   // kernel-uniform
+    part[g][tx] = ua;
+    __syncthreads();
+    if (g == 0 && ok) {
+      float us = 0.f;
+#pragma unroll
+      for (int q = 0; q < kMcGroups; ++q) us += part[q][tx];
+      u[(long long)b * d + j] = us * inv;
+    }
+  }
 }
 
 // ------------------------------------------------------------ trace, dots
@@ -827,7 +932,7 @@ __global__ void pool_bwd_rows_kernel(const float* __restrict__ dZc, const float*
 __global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
                                    const float* __restrict__ dw, const float* __restrict__ dt,
                                    const float* __restrict__ G, const float* __restrict__ s, int n,
-                                   float* __restrict__ ds) {
+                                   int sym, float* __restrict__ ds) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
   if (row >= n) return;
@@ -839,10 +944,18 @@ __global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
   const float dtb = dt[b];
   const int i = row;
   float a = 0.f;
-  for (int j = lane; j < n; j += 32) {
-    const float dij = dWb[(long long)i * ldW + j] + dwb[i] + (i == j ? dtb : 0.f);
-    const float dji = dWb[(long long)j * ldW + i] + dwb[j] + (i == j ? dtb : 0.f);
-    a += (dij * Gb[(long long)i * n + j] + dji * Gb[(long long)j * n + i]) * sb[j];
+  if (sym) {
+    // G and dW symmetric (EGM_MHD_SYMMETRIC_GRAPH): the mirrored elements are the row's own
+    for (int j = lane; j < n; j += 32) {
+      const float d = dWb[(long long)i * ldW + j] + (i == j ? dtb : 0.f);
+      a += (2.f * d + dwb[i] + dwb[j]) * Gb[(long long)i * n + j] * sb[j];
+    }
+  } else {
+    for (int j = lane; j < n; j += 32) {
+      const float dij = dWb[(long long)i * ldW + j] + dwb[i] + (i == j ? dtb : 0.f);
+      const float dji = dWb[(long long)j * ldW + i] + dwb[j] + (i == j ? dtb : 0.f);
+      a += (dij * Gb[(long long)i * n + j] + dji * Gb[(long long)j * n + i]) * sb[j];
+    }
   }
   a = warp_sum(a);
   if (lane == 0) ds[(long long)b * n + i] = a;
@@ -850,15 +963,24 @@ __global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
 __global__ void pool_bwd_dG_kernel(const float* __restrict__ dW, long long ldW,
                                    const float* __restrict__ dw, const float* __restrict__ dt,
                                    const float* __restrict__ s, const float* __restrict__ deg,
-                                   const float* __restrict__ ds, int n, float eps,
+                                   const float* __restrict__ ds, int n, float eps, int sym,
                                    float* __restrict__ dG) {
   const int b = blockIdx.z, i = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const float si = s[(long long)b * n + i], sj = s[(long long)b * n + j];
-  const float dwf = dW[((long long)b * n + i) * ldW + j] + dw[(long long)b * n + i] + (i == j ? dt[b] : 0.f);
   // s = max(deg,eps)^(-1/2): d s/d deg = -0.5 s^3 where the clamp is inactive (deg >= eps)
   const float ddeg = (deg[(long long)b * n + i] >= eps) ? -0.5f * si * si * si * ds[(long long)b * n + i] : 0.f;
+  if (sym) {
+    // symmetric graph: return the symmetric part (dG + dG^T)/2 of the reference's gradient, i.e. the
+    // gradient with respect to a symmetric matrix (dW is symmetric here; row terms are averaged)
+    const float ddegj = (deg[(long long)b * n + j] >= eps) ? -0.5f * sj * sj * sj * ds[(long long)b * n + j] : 0.f;
+    const float dwf = dW[((long long)b * n + i) * ldW + j] +
+                      0.5f * (dw[(long long)b * n + i] + dw[(long long)b * n + j]) + (i == j ? dt[b] : 0.f);
+    dG[((long long)b * n + i) * n + j] = si * dwf * sj + 0.5f * (ddeg + ddegj);
+    return;
+  }
+  const float dwf = dW[((long long)b * n + i) * ldW + j] + dw[(long long)b * n + i] + (i == j ? dt[b] : 0.f);
   dG[((long long)b * n + i) * n + j] = si * dwf * sj + ddeg;
 }
 
@@ -900,19 +1022,19 @@ void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, 
 }
 void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
                   int symmetric, int batch, int n, float* G, cudaStream_t st) {
-  dim3 grid((n + 127) / 128, n, batch);
+  dim3 grid(poly_pairs(n), batch);
   if (P <= 3 && Q <= 3)
-    gpf_poly_fwd_kernel<3><<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+    gpf_poly_fwd_kernel<3><<<grid, 256, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
   else
-    gpf_poly_fwd_kernel<kMaxDeg><<<grid, 128, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+    gpf_poly_fwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
   note_launch();
 }
-int gpf_poly_bwd_blocks(int batch, int n) { return batch * ((n + kPolyBwdRows - 1) / kPolyBwdRows); }
+int gpf_poly_bwd_blocks(int batch, int n) { return batch * poly_pairs(n); }
 void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
                   const float* coef, int P, int Q, int symmetric, int batch, int n, const W& Ea,
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
                   cudaStream_t st) {
-  dim3 grid((n + kPolyBwdRows - 1) / kPolyBwdRows, batch);
+  dim3 grid(poly_pairs(n), batch);
   if (P <= 3 && Q <= 3)
     gpf_poly_bwd_kernel<3><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
                                                  wptr(Ep, prec), partial);
@@ -938,9 +1060,9 @@ void weight(const float* G, const float* s, int batch, int n, const W& Wn, float
 void mean_center(const float* Z, const float* w, const float* wdiag, int batch, int n, int d,
                  float eps, float* t, float* sw, float* mu, float* u, const W& Zc, int prec,
                  cudaStream_t st) {
-  dim3 grid((d + 127) / 128, batch);
-  mean_center_kernel<<<grid, 128, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu, u,
-                                                           wptr(Zc, prec));
+  dim3 grid((d + kMcCols - 1) / kMcCols, batch);
+  mean_center_kernel<<<grid, kMcCols * kMcGroups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
+                                                                           u, wptr(Zc, prec));
   note_launch();
 }
 void trace_scales(const float* M, int batch, int d, float eps, int post_mode, float* tr, float* inv,
@@ -1048,16 +1170,16 @@ void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w
   note_launch();
 }
 void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* dt, const float* G,
-                 const float* s, int batch, int n, float* ds, cudaStream_t st) {
+                 const float* s, int batch, int n, int sym, float* ds, cudaStream_t st) {
   dim3 grid((n + 7) / 8, batch);
-  pool_bwd_ds_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, G, s, n, ds);
+  pool_bwd_ds_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, G, s, n, sym, ds);
   note_launch();
 }
 void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
-                 const float* deg, const float* ds, int batch, int n, float eps, float* dG,
+                 const float* deg, const float* ds, int batch, int n, float eps, int sym, float* dG,
                  cudaStream_t st) {
   dim3 grid((n + 127) / 128, n, batch);
-  pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, dG);
+  pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, sym, dG);
   note_launch();
 }
 

@@ -154,11 +154,13 @@ void pool_bwd_rows(const float* dZc, const float* Z, const W& Zc, const float* w
                    int n, int d, float eps, float* dZ, float* dw, float* dt, int prec,
                    cudaStream_t st);
 // ds_i = sum_j (dWf_ij G_ij s_j + dWf_ji G_ji s_j),  dWf = dW + dw 1^T + dt I
+// sym: G and dW are symmetric - no mirrored reads
 void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* dt, const float* G,
-                 const float* s, int batch, int n, float* ds, cudaStream_t st);
+                 const float* s, int batch, int n, int sym, float* ds, cudaStream_t st);
 // dG_ij = s_i dWf_ij s_j + ddeg_i ;  ddeg = -0.5 * s^3 * ds * [deg >= eps]
+// sym: the symmetric part (dG + dG^T)/2 of that gradient (dW symmetric)
 void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
-                 const float* deg, const float* ds, int batch, int n, float eps, float* dG,
+                 const float* deg, const float* ds, int batch, int n, float eps, int sym, float* dG,
                  cudaStream_t st);
 
 }  // namespace k

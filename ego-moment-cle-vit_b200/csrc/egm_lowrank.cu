@@ -274,8 +274,8 @@ int egm_mlr_bwd(const float* dO, const float* dv, const float* dotOO_in, const f
   PoolVecs pv(const_cast<float*>(vecs), B, N);
   k::pool_bwd_dmu(dZc, du, pv.sw, pv.t, B, N, D, eps, dmu, st);
   k::pool_bwd_rows(dZc, Z, Zc, pv.w, pv.t, mu, u, du, dmu, B, N, D, eps, dZ, dw, dt, prec, st);
-  k::pool_bwd_ds(dW, ldW, dw, dt, G, pv.s, B, N, ds, st);
-  k::pool_bwd_dG(dW, ldW, dw, dt, pv.s, pv.deg, ds, B, N, eps, dG, st);
+  k::pool_bwd_ds(dW, ldW, dw, dt, G, pv.s, B, N, 0, ds, st);
+  k::pool_bwd_dG(dW, ldW, dw, dt, pv.s, pv.deg, ds, B, N, eps, 0, dG, st);
   EGM_LAUNCHED();
   return EGM_OK;
 }

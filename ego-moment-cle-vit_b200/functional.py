@@ -371,8 +371,9 @@ _symmetric_fast_path = os.environ.get("EGM_SYMMETRIC_FAST_PATH", "1") != "0"
 def set_symmetric_fast_path(on: bool) -> None:
     """Let MomentHead exploit a graph tagged exactly symmetric (default on): every Newton-Schulz
     product then evaluates its upper tiles only and the backward runs as a symmetric tangent.
-    With the fast path the gradient returned for the graph is the reference's plus a skew-symmetric
-    matrix, which the symmetrisation inside GraphPolynomialFusion's backward removes."""
+    With the fast path the gradient returned for the graph is the symmetric part (dG + dG^T)/2 of the
+    reference's (the gradient with respect to a symmetric matrix) - exactly what the symmetrisation in
+    GraphPolynomialFusion's backward lets through, so token and parameter gradients are unchanged."""
     global _symmetric_fast_path
     _symmetric_fast_path = bool(on)
 

@@ -138,8 +138,9 @@ int egm_mlr_bwd(const float* dO, const float* dv, const float* dotOO, const floa
  * symmetric_enforce, gpf_kernel.py:150-152). Every matrix of the Newton-Schulz chain is then symmetric:
  * only the upper 256 x 256 blocks of each product are evaluated and stored (6 of 9 tiles at D = 768),
  * and the backward runs as a symmetric forward tangent (the Frechet derivative of a matrix polynomial
- * at a symmetric point is self-adjoint). dZ is the same; dG differs from the general path by a
- * skew-symmetric matrix, i.e. (dG + dG^T)/2 - all a symmetric-graph producer consumes - is the same.
+ * at a symmetric point is self-adjoint). dZ is the same; dG is the SYMMETRIC PART (dG + dG^T)/2 of the
+ * general path's gradient - the gradient with respect to a symmetric matrix, and all that a
+ * symmetric-graph producer (gpf_kernel.py:150-152, whose backward symmetrises) consumes.
  * The same flags value must be passed to the matching backward. */
 enum { EGM_MHD_SYMMETRIC_GRAPH = 1 };
 size_t egm_mhd_state_bytes(int B, int N, int D, int iters, int prec);
