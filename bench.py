@@ -40,9 +40,11 @@ if ROOT not in sys.path:
 METRIC = "MomentHead+GPF fwd+bwd images/sec"
 UNIT = "images/s"
 N_TOK, D_IN, D_OUT, DEG, NS_ITERS = 197, 768, 256, 3, 5
+DEGS = (DEG, DEG)
 
 
 def parse():
+    global N_TOK, D_IN, DEGS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -52,18 +54,25 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--algorithm", default="dense", choices=["dense", "lowrank"],
                     help="iSQRT-COV evaluation: D x D Newton-Schulz chain, or the N x N low-rank form")
+    ap.add_argument("--tokens", type=int, default=N_TOK, help="tokens per image (197 ViT-B/16; 144 Swin-B 384 px)")
+    ap.add_argument("--d-in", type=int, default=D_IN, help="token width (768 ViT-B; 1024 Swin-B)")
+    ap.add_argument("--degree", type=int, nargs=2, default=[DEG, DEG], metavar=("P", "Q"),
+                    help="GPF polynomial degrees (BASELINE configs[4] sweeps (1,1)...(3,3))")
     ap.add_argument("--no-extras", action="store_true", help="skip bf16-mode / cpu-baseline side runs")
     ap.add_argument("--gemm-breakdown", action="store_true",
                     help="print the per-shape time of the GEMM-engine launches to stderr")
-    return ap.parse_args()
+    args = ap.parse_args()
+    N_TOK, D_IN, DEGS = args.tokens, args.d_in, tuple(args.degree)   # the named workload unless overridden
+    return args
 
 
 def workload_config(args, extra=None):
     cfg = {
-        "workload": "configs[1]: MomentHead+GPFKernel (degree 3, 2nd-order iSQRT-COV, 5 NS iters) fwd+bwd, "
-                    f"B={args.batch}/GPU, N={N_TOK}, D={D_IN}->d_out={D_OUT}",
+        "workload": ("configs[1]" if (N_TOK, D_IN, tuple(args.degree)) == (197, 768, (DEG, DEG)) else "custom shape") +
+                    f": MomentHead+GPFKernel (degree {args.degree[0]},{args.degree[1]}, 2nd-order iSQRT-COV, "
+                    f"5 NS iters) fwd+bwd, B={args.batch}/GPU, N={N_TOK}, D={D_IN}->d_out={D_OUT}",
         "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "tokens": N_TOK,
-        "d_in": D_IN, "d_out": D_OUT, "gpf_degree": [DEG, DEG], "ns_iterations": NS_ITERS,
+        "d_in": D_IN, "d_out": D_OUT, "gpf_degree": list(args.degree), "ns_iterations": NS_ITERS,
         "parallelism": f"dp{args.gpus} (batch sharded per image, NCCL gradient all-reduce)",
         "step": "forward + backward + grad all-reduce + SGD update, train-mode BN, dropout 0.1",
     }
@@ -126,7 +135,7 @@ def cpu_port_setup(batch, seed=0):
     import torch
     pkg = importlib.import_module("ego-moment-cle-vit_b200")
     torch.manual_seed(seed)
-    gpf = pkg.GraphPolynomialFusion(DEG, DEG)
+    gpf = pkg.GraphPolynomialFusion(*DEGS)
     head = pkg.MomentHead(D_IN, D_OUT, use_third_order=False, isqrt_iterations=NS_ITERS)
     params = {k: v.detach().numpy() for k, v in head.state_dict().items()}
     g = torch.Generator().manual_seed(1234)
@@ -212,7 +221,7 @@ def run_native(args):
     EF.set_precision(args.precision)
     EF.set_ns_algorithm(args.algorithm)
     torch.manual_seed(0)
-    gpf = pkg.GraphPolynomialFusion(DEG, DEG).to(dev)
+    gpf = pkg.GraphPolynomialFusion(args.degree[0], args.degree[1]).to(dev)
     head = pkg.MomentHead(D_IN, D_OUT, use_third_order=False, isqrt_iterations=NS_ITERS).to(dev).train()
     egm_dist.broadcast_parameters(gpf)
     egm_dist.broadcast_parameters(head)

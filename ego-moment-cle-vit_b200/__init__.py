@@ -9,11 +9,11 @@ from . import _lib, functional
 from .functional import get_ns_algorithm, get_precision, precision, set_ns_algorithm, set_precision
 from .models import (AdaptiveGraphPolynomialFusion, GPFKernel, GraphPolynomialFusion, MomentHead,
                      NewtonSchulzSqrtm, TensorSketch)
-from .dropin import install_into
+from .dropin import install_into, patch_alignment_loss
 
 __version__ = "0.1.0"
 __all__ = [
     'GraphPolynomialFusion', 'AdaptiveGraphPolynomialFusion', 'GPFKernel', 'MomentHead',
     'NewtonSchulzSqrtm', 'TensorSketch', 'functional', 'set_precision', 'get_precision',
-    'precision', 'set_ns_algorithm', 'get_ns_algorithm', 'install_into',
+    'precision', 'set_ns_algorithm', 'get_ns_algorithm', 'install_into', 'patch_alignment_loss',
 ]

@@ -39,9 +39,12 @@ SIGNATURES = {
     "egm_prof_read": (_I, [_I, _P, _P, _P]),
     "egm_gpf_ldr": (_LL, [_I]),
     "egm_gpf_fwd_workspace": (_Z, [_I, _I, _I, _I]),
-    "egm_gpf_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "egm_gpf_state_bytes": (_Z, [_I, _I, _I, _I]),
+    "egm_align_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "egm_align_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
+    "egm_gpf_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_gpf_bwd_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
-    "egm_gpf_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _I, _P, _Z, _P]),
+    "egm_gpf_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _I, _P, _Z, _P]),
     "egm_pool_state_bytes": (_Z, [_I, _I, _I, _I]),
     "egm_pool_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_pool_fwd": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _I, _P, _Z, _P]),

@@ -302,10 +302,17 @@ size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec) {
   (void)prec;
   return 2 * pad256(w_bytes(B, N, D)) + 512;
 }
+size_t egm_gpf_state_bytes(int B, int N, int D, int prec) {
+  (void)prec;
+  return 2 * pad256(w_bytes(B, N, D)) + 256;
+}
 
 int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
                 int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
-                float* nrm_p, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+                float* nrm_p, void* xn_state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  // the normalised tokens (GEMM operand planes) go to `xn_state` when the caller keeps them for the
+  // backward, else to scratch
+  if (xn_state) { ws = xn_state; ws_bytes = egm_gpf_state_bytes(B, N, D, prec); }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_fwd: unknown precision mode %d", prec);
   EGM_REQUIRE(a && p && coef && G && Ra && Rp && nrm_a && nrm_p, EGM_ERR_ARG, "egm_gpf_fwd: null pointer");
@@ -340,9 +347,9 @@ size_t egm_gpf_bwd_workspace(int B, int N, int D, int P, int Q, int prec) {
 }
 
 int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* coef, const float* Ra,
-                const float* Rp, const float* nrm_a, const float* nrm_p, int B, int N, int D, int P,
-                int Q, int cosine, float eps, int symmetric, float* da, float* dp, float* dcoef,
-                int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+                const float* Rp, const float* nrm_a, const float* nrm_p, const void* xn_state, int B,
+                int N, int D, int P, int Q, int cosine, float eps, int symmetric, float* da, float* dp,
+                float* dcoef, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_bwd: unknown precision mode %d", prec);
   EGM_REQUIRE(dG && a && p && coef && Ra && Rp && nrm_a && nrm_p && da && dp && dcoef, EGM_ERR_ARG,
@@ -362,16 +369,21 @@ int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* co
   const W Ea = make_w(wea, B, N, N), Ep = make_w(wep, B, N, N), Xn = make_w(wx, B, N, D);
   k::gpf_poly_bwd(dG, Ra, Rp, ldR, coef, P, Q, symmetric, B, N, Ea, Ep, partial, nblocks, dcoef, prec, st);
   EGM_LAUNCHED();
+  Arena xs(const_cast<void*>(xn_state), xn_state ? egm_gpf_state_bytes(B, N, D, prec) : 0);
+  const W An = make_w(xs.take(w_bytes(B, N, D)), B, N, D), Pn = make_w(xs.take(w_bytes(B, N, D)), B, N, D);
   for (int v = 0; v < 2; ++v) {
     const float* x = v ? p : a;
     const float* nrm = v ? nrm_p : nrm_a;
     float* dx = v ? dp : da;
-    // re-materialise the normalised tokens (cheaper than keeping 2 x [B,N,D] alive)
-    k::rownorm(x, B, N, D, eps, cosine, dxn /*norms scratch, overwritten below*/, Xn, prec, st);
-    EGM_LAUNCHED();
+    if (!xn_state) {
+      // memory-saving mode: re-materialise the normalised tokens instead of keeping 2 x [B,N,D] alive
+      k::rownorm(x, B, N, D, eps, cosine, dxn /*norms scratch, overwritten below*/, Xn, prec, st);
+      EGM_LAUNCHED();
+    }
+    const W& Xv = xn_state ? (v ? Pn : An) : Xn;
     GemmProblem g;  // d An = (dR + dR^T) An
     g.M = N; g.N = D; g.batch = B; g.nterms = 1;
-    g.t[0] = term(v ? Ep : Ea, 0, Xn, 0, N, prec);
+    g.t[0] = term(v ? Ep : Ea, 0, Xv, 0, N, prec);
     g.Cf = f32_mat(cosine ? dxn : dx, N, D, D, (long long)N * D);
     EGM_CUDA(run_gemm(g, prec, st));
     if (cosine) {
@@ -873,6 +885,25 @@ int egm_normalize_graph(const float* G, int B, int N, int method, float eps, flo
 int egm_batch_trace(const float* M, int B, int D, float* tr, egm_stream_t stream) {
   EGM_REQUIRE(M && tr && B > 0 && D > 0, EGM_ERR_ARG, "egm_batch_trace: bad argument");
   k::batch_trace(M, B, D, tr, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+
+// ============================================================= graph alignment loss
+int egm_align_fwd(const float* G, const long long* labels, int B, int N, float* g, float* dg,
+                  float* rowloss, float* loss, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(G && labels && g && dg && rowloss && loss && B > 0 && N > 0, EGM_ERR_ARG,
+              "egm_align_fwd: bad argument");
+  k::graph_mean(G, B, (long long)N * N, g, st);
+  k::align_rows(g, labels, B, rowloss, dg, st);
+  k::sum_partials(rowloss, B, 1, loss, st);
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_align_bwd(const float* dg, const float* dloss, int B, int N, float* dG, egm_stream_t stream) {
+  EGM_REQUIRE(dg && dloss && dG && B > 0 && N > 0, EGM_ERR_ARG, "egm_align_bwd: bad argument");
+  k::align_bwd(dg, dloss, B, (long long)N * N, dG, static_cast<cudaStream_t>(stream));
   EGM_LAUNCHED();
   return EGM_OK;
 }

@@ -66,6 +66,21 @@ __device__ __forceinline__ void wstore4(const WPtr& p, long long off, float4 x) 
     }
   }
 }
+__device__ __forceinline__ void wstore2(const WPtr& p, long long off, float x0, float x1) {
+  if (p.f) {
+    *reinterpret_cast<float2*>(p.f + off) = make_float2(x0, x1);
+  } else {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    *reinterpret_cast<uint32_t*>(p.hi + off) =
+        __bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    if (p.lo) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      *reinterpret_cast<uint32_t*>(p.lo + off) =
+          __bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+}
 __device__ __forceinline__ float wload(const WPtr& p, long long off) {
   if (p.f) return p.f[off];
   float x = __bfloat162float(p.hi[off]);
@@ -219,6 +234,34 @@ __device__ __forceinline__ float poly_eval(const float (&pa)[MD + 1], const floa
   return f;
 }
 
+// f = sum_pq c_pq pa_p pb_q together with df/da-side = sum_pq c_pq da_p pb_q and df/db-side =
+// sum_pq c_pq pa_p db_q, sharing the inner sums. `cp` is the coefficient table padded with zeros to
+// (MD+1) x (MD+1), so no degree tests are needed (powers above the degree are zero as well).
+template <int MD>
+__device__ __forceinline__ void poly_eval_grad(const float (&pa)[MD + 1], const float (&pb)[MD + 1],
+                                               const float (&da)[MD + 1], const float (&db)[MD + 1],
+                                               const float* cp, float& f, float& dfa, float& dfb) {
+  float colsum[MD + 1];   // sum_p c_pq pa_p
+#pragma unroll
+  for (int q = 0; q <= MD; ++q) colsum[q] = 0.f;
+  f = 0.f; dfa = 0.f;
+#pragma unroll
+  for (int p = 0; p <= MD; ++p) {
+    float inner = 0.f;    // sum_q c_pq pb_q
+#pragma unroll
+    for (int q = 0; q <= MD; ++q) {
+      const float cpq = cp[p * (MD + 1) + q];
+      inner = fmaf(cpq, pb[q], inner);
+      colsum[q] = fmaf(cpq, pa[p], colsum[q]);
+    }
+    f = fmaf(pa[p], inner, f);
+    dfa = fmaf(da[p], inner, dfa);
+  }
+  dfb = 0.f;
+#pragma unroll
+  for (int q = 0; q <= MD; ++q) dfb = fmaf(db[q], colsum[q], dfb);
+}
+
 // The polynomial kernels work on PAIRS of 32 x 32 tiles, (ti,tj) and its mirror (tj,ti), ti <= tj:
 // the mirror tile is staged in shared memory with coalesced loads and read transposed, so a thread
 // owns the element pair (i,j)/(j,i), evaluates it once, writes (i,j) directly and hands (j,i) back
@@ -286,17 +329,21 @@ gpf_poly_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp, 
 
 // one block per tile pair of one image; deterministic two-stage dcoef reduction
 template <int MD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MD <= 3) ? 4 : 1)
 gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
                     const float* __restrict__ Rp, long long ldR, const float* __restrict__ coef,
                     int P, int Q, int symmetric, int n, WPtr Ea, WPtr Ep,
                     float* __restrict__ partial) {
-  __shared__ float c[(kMaxDeg + 1) * (kMaxDeg + 1)];
-  __shared__ float red[(kMaxDeg + 1) * (kMaxDeg + 1)];
+  __shared__ float cp[(MD + 1) * (MD + 1)];    // coefficients, zero-padded to (MD+1)^2
+  __shared__ float red[(MD <= 3) ? 1 : (MD + 1) * (MD + 1)];
   __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1], sg[kPT][kPT + 1];
   __shared__ float wacc[8][16];
   const int nterm = (P + 1) * (Q + 1);
-  for (int t = threadIdx.x; t < nterm; t += blockDim.x) { c[t] = coef[t]; red[t] = 0.f; }
+  for (int t = threadIdx.x; t < (MD + 1) * (MD + 1); t += blockDim.x) {
+    const int pp = t / (MD + 1), qq = t % (MD + 1);
+    cp[t] = (pp <= P && qq <= Q) ? coef[pp * (Q + 1) + qq] : 0.f;
+    if (MD > 3) red[t] = 0.f;
+  }
   const int b = blockIdx.y;
   int ti, tj;
   poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
@@ -312,6 +359,16 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
     sp[r][tx] = ok ? Rp[rb + (long long)i2 * ldR + j2] : 0.f;
     sg[r][tx] = ok ? dG[gb + (long long)i2 * n + j2] : 0.f;
   }
+  // this thread's own elements: issue the loads before the barrier
+  float ra_k[4], rp_k[4], g_k[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = ti * kPT + ty + 8 * k, j = tj * kPT + tx;
+    const bool ok = i < n && j < n;
+    ra_k[k] = ok ? Ra[rb + (long long)i * ldR + j] : 0.f;
+    rp_k[k] = ok ? Rp[rb + (long long)i * ldR + j] : 0.f;
+    g_k[k] = ok ? dG[gb + (long long)i * n + j] : 0.f;
+  }
   __syncthreads();
   // small-degree fast path keeps the per-term sums in registers
   float acc[16];
@@ -323,13 +380,18 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
     const int r = ty + 8 * k, i = ti * kPT + r, j = tj * kPT + tx;
     ea_k[k] = ep_k[k] = 0.f;
     if (i < n && j < n) {
-      float pa[MD + 1], pb[MD + 1], pat[MD + 1], pbt[MD + 1];
-      const float ra = Ra[rb + (long long)i * ldR + j], rp = Rp[rb + (long long)i * ldR + j];
+      float pa[MD + 1], pb[MD + 1], da[MD + 1], db[MD + 1];
+      float pat[MD + 1], pbt[MD + 1], dat[MD + 1], dbt[MD + 1];
+      const float ra = ra_k[k], rp = rp_k[k];
       const float rat = sa[tx][r], rpt = sp[tx][r];
       had_powers<MD>(ra, P, pa); had_powers<MD>(rp, Q, pb);
+      had_dpowers<MD>(ra, P, da); had_dpowers<MD>(rp, Q, db);
       had_powers<MD>(rat, P, pat); had_powers<MD>(rpt, Q, pbt);
-      const float f = poly_eval<MD>(pa, pb, c, P, Q), ft = poly_eval<MD>(pat, pbt, c, P, Q);
-      const float g_ij = dG[gb + (long long)i * n + j], g_ji = sg[tx][r];
+      had_dpowers<MD>(rat, P, dat); had_dpowers<MD>(rpt, Q, dbt);
+      float f, fa, fb, ft, fat, fbt;
+      poly_eval_grad<MD>(pa, pb, da, db, cp, f, fa, fb);
+      poly_eval_grad<MD>(pat, pbt, dat, dbt, cp, ft, fat, fbt);
+      const float g_ij = g_k[k], g_ji = sg[tx][r];
       float dF_ij, dF_ji;
       if (symmetric) {
         const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
@@ -339,11 +401,8 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
         dF_ji = (ft >= 0.f) ? g_ji : 0.f;
       }
       // E = dR + dR^T is symmetric: the same value goes to (i,j) and (j,i)
-      float da[MD + 1], db[MD + 1], dat[MD + 1], dbt[MD + 1];
-      had_dpowers<MD>(ra, P, da); had_dpowers<MD>(rp, Q, db);
-      had_dpowers<MD>(rat, P, dat); had_dpowers<MD>(rpt, Q, dbt);
-      const float ea = dF_ij * poly_eval<MD>(da, pb, c, P, Q) + dF_ji * poly_eval<MD>(dat, pbt, c, P, Q);
-      const float ep = dF_ij * poly_eval<MD>(pa, db, c, P, Q) + dF_ji * poly_eval<MD>(pat, dbt, c, P, Q);
+      const float ea = dF_ij * fa + dF_ji * fat;
+      const float ep = dF_ij * fb + dF_ji * fbt;
       ea_k[k] = ea; ep_k[k] = ep;
       wstore(Ea, (long long)b * Ea.bs + (long long)i * Ea.ld + j, ea);
       wstore(Ep, (long long)b * Ep.bs + (long long)i * Ep.ld + j, ep);
@@ -352,14 +411,15 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
       if (MD == 3) {
         // acc[4p+q]: static register indices; re-packed to the (Q+1)-strided order on output
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp)
+        for (int pp = 0; pp < 4; ++pp) {
+          const float u = dF_ij * pa[pp], v = dF_m * pat[pp];
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-            acc[pp * 4 + qq] += dF_ij * (pa[pp] * pb[qq]) + dF_m * (pat[pp] * pbt[qq]);
+          for (int qq = 0; qq < 4; ++qq) acc[pp * 4 + qq] = fmaf(u, pb[qq], fmaf(v, pbt[qq], acc[pp * 4 + qq]));
+        }
       } else {
         for (int pp = 0; pp <= P; ++pp)
           for (int qq = 0; qq <= Q; ++qq)
-            atomicAdd(&red[pp * (Q + 1) + qq], dF_ij * pa[pp] * pb[qq] + dF_m * pat[pp] * pbt[qq]);
+            atomicAdd(&red[pp * (MD + 1) + qq], dF_ij * pa[pp] * pb[qq] + dF_m * pat[pp] * pbt[qq]);
       }
     }
   }
@@ -396,9 +456,201 @@ gpf_poly_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
     }
   } else {
     __syncthreads();
-    for (int t = threadIdx.x; t < nterm; t += blockDim.x) out[t] = red[t];
+    for (int t = threadIdx.x; t < (MD + 1) * (MD + 1); t += blockDim.x) {
+      const int pp = t / (MD + 1), qq = t % (MD + 1);
+      if (pp <= P && qq <= Q) out[pp * (Q + 1) + qq] = red[t];
+    }
   }
 }
+// ---- degree <= 3 (the configurations of the reference: configs/ufg_base.yaml sweeps (1,1)..(3,3)):
+// the 4 x 4 zero-padded coefficient table lives in registers and the polynomial is two nested Horner
+// forms, ~20 FMA per evaluation instead of a shared-memory read per term.
+struct Poly3 {
+  float c[16];
+  __device__ __forceinline__ void load(const float* __restrict__ coef, int P, int Q) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[p * 4 + q] = (p <= P && q <= Q) ? coef[p * (Q + 1) + q] : 0.f;
+  }
+  // inner_p = sum_q c_pq f_q(y)
+  __device__ __forceinline__ void inner(float y, float y2, float y3, float (&in)[4]) const {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) in[p] = fmaf(c[p * 4 + 3], y3, fmaf(c[p * 4 + 2], y2, fmaf(c[p * 4 + 1], y, c[p * 4])));
+  }
+  // f = sum_pq c_pq f_p(x) f_q(y);  f_0 = 1, f_1 = t, f_k = max(t,0)^k
+  __device__ __forceinline__ float eval(float x, float y) const {
+    const float cx = fmaxf(x, 0.f), cy = fmaxf(y, 0.f);
+    const float x2 = cx * cx, x3 = x2 * cx, y2 = cy * cy, y3 = y2 * cy;
+    float in[4];
+    inner(y, y2, y3, in);
+    return fmaf(in[3], x3, fmaf(in[2], x2, fmaf(in[1], x, in[0])));
+  }
+  // f, df/dx, df/dy and the power tables pa = f_p(x), pb = f_q(y)
+  __device__ __forceinline__ void eval_grad(float x, float y, float& f, float& fx, float& fy,
+                                            float (&pa)[4], float (&pb)[4]) const {
+    const float cx = fmaxf(x, 0.f), cy = fmaxf(y, 0.f);
+    pa[0] = 1.f; pa[1] = x; pa[2] = cx * cx; pa[3] = pa[2] * cx;
+    pb[0] = 1.f; pb[1] = y; pb[2] = cy * cy; pb[3] = pb[2] * cy;
+    float in[4];
+    inner(y, pb[2], pb[3], in);
+    f = fmaf(in[3], pa[3], fmaf(in[2], pa[2], fmaf(in[1], x, in[0])));
+    fx = fmaf(3.f * pa[2], in[3], fmaf(2.f * cx, in[2], in[1]));      // f'_1 = 1, f'_k = k max(t,0)^(k-1)
+    float col[3];                                                     // col_q = sum_p c_pq f_p(x), q = 1..3
+#pragma unroll
+    for (int q = 1; q < 4; ++q) col[q - 1] = fmaf(c[12 + q], pa[3], fmaf(c[8 + q], pa[2], fmaf(c[4 + q], x, c[q])));
+    fy = fmaf(3.f * pb[2], col[2], fmaf(2.f * cy, col[1], col[0]));
+  }
+};
+
+__global__ void __launch_bounds__(256)
+gpf_poly3_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp, int ldR,
+                     const float* __restrict__ coef, int P, int Q, int symmetric, int n,
+                     float* __restrict__ G) {
+  __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1];
+  Poly3 poly;
+  poly.load(coef, P, Q);
+  int ti, tj;
+  poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* ra_b = Ra + (long long)blockIdx.y * n * ldR;
+  const float* rp_b = Rp + (long long)blockIdx.y * n * ldR;
+  float* g_b = G + (long long)blockIdx.y * n * n;
+  const int i0 = ti * kPT, j0 = tj * kPT;
+  float xa[4], xp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    const bool okm = (j0 + r < n) && (i0 + tx < n);     // mirror tile (tj, ti)
+    sa[r][tx] = okm ? ra_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    sp[r][tx] = okm ? rp_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    const bool ok = (i0 + r < n) && (j0 + tx < n);
+    xa[k] = ok ? ra_b[(i0 + r) * ldR + j0 + tx] : 0.f;
+    xp[k] = ok ? rp_b[(i0 + r) * ldR + j0 + tx] : 0.f;
+  }
+  __syncthreads();
+  float g2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    const float f = poly.eval(xa[k], xp[k]);
+    const float ft = poly.eval(sa[tx][r], sp[tx][r]);
+    const float g1 = fmaxf(symmetric ? 0.5f * (f + ft) : f, 0.f);
+    g2[k] = symmetric ? g1 : fmaxf(ft, 0.f);
+    if ((i0 + r < n) && (j0 + tx < n)) g_b[(i0 + r) * n + j0 + tx] = g1;
+  }
+  if (ti == tj) return;   // block-uniform: a diagonal tile is its own mirror
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sa[tx][ty + 8 * k] = g2[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    if ((j0 + r < n) && (i0 + tx < n)) g_b[(j0 + r) * n + i0 + tx] = sa[r][tx];
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
+                     const float* __restrict__ Rp, int ldR, const float* __restrict__ coef, int P, int Q,
+                     int symmetric, int n, WPtr Ea, WPtr Ep, float* __restrict__ partial) {
+  __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1], sg[kPT][kPT + 1];
+  __shared__ float wacc[8][16];
+  Poly3 poly;
+  poly.load(coef, P, Q);
+  int ti, tj;
+  poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  const bool offdiag = ti != tj;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* ra_b = Ra + (long long)blockIdx.y * n * ldR;
+  const float* rp_b = Rp + (long long)blockIdx.y * n * ldR;
+  const float* dg_b = dG + (long long)blockIdx.y * n * n;
+  const int i0 = ti * kPT, j0 = tj * kPT;
+  float xa[4], xp[4], xg[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    const bool okm = (j0 + r < n) && (i0 + tx < n);     // mirror tile (tj, ti)
+    sa[r][tx] = okm ? ra_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    sp[r][tx] = okm ? rp_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    sg[r][tx] = okm ? dg_b[(j0 + r) * n + i0 + tx] : 0.f;
+    const bool ok = (i0 + r < n) && (j0 + tx < n);
+    xa[k] = ok ? ra_b[(i0 + r) * ldR + j0 + tx] : 0.f;
+    xp[k] = ok ? rp_b[(i0 + r) * ldR + j0 + tx] : 0.f;
+    xg[k] = ok ? dg_b[(i0 + r) * n + j0 + tx] : 0.f;
+  }
+  __syncthreads();
+  float acc[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+  float ea_k[4], ep_k[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = ty + 8 * k;
+    float f, fa, fb, ft, fat, fbt, pa[4], pb[4], pat[4], pbt[4];
+    poly.eval_grad(xa[k], xp[k], f, fa, fb, pa, pb);
+    poly.eval_grad(sa[tx][r], sp[tx][r], ft, fat, fbt, pat, pbt);
+    const float g_ij = xg[k], g_ji = sg[tx][r];       // both zero outside the matrix
+    float dF_ij, dF_ji;
+    if (symmetric) {
+      const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
+      dF_ij = dF_ji = 0.5f * (g_ij + g_ji) * sgate;
+    } else {
+      dF_ij = (f >= 0.f) ? g_ij : 0.f;
+      dF_ji = (ft >= 0.f) ? g_ji : 0.f;
+    }
+    // E = dR + dR^T is symmetric: the same value goes to (i,j) and (j,i)
+    ea_k[k] = dF_ij * fa + dF_ji * fat;
+    ep_k[k] = dF_ij * fb + dF_ji * fbt;
+    // dcoef: this thread's (i,j) term, plus the (j,i) term when the mirror tile is not this tile
+    const float dF_m = offdiag ? dF_ji : 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const float u = dF_ij * pa[pp], v = dF_m * pat[pp];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) acc[pp * 4 + qq] = fmaf(u, pb[qq], fmaf(v, pbt[qq], acc[pp * 4 + qq]));
+    }
+  }
+  // stage the tile of E in shared memory; rows leave as 4-column groups (one 8-byte store per plane),
+  // the mirror tile as the transposed read of the same staging tile
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sa[ty + 8 * k][tx] = ea_k[k]; sp[ty + 8 * k][tx] = ep_k[k]; }
+  __syncthreads();
+  {
+    const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
+    const long long eb = (long long)blockIdx.y * Ea.bs;
+    if (i0 + r < n && j0 + c < n) {
+      const long long o = eb + (long long)(i0 + r) * Ea.ld + j0 + c;
+      wstore4(Ea, o, make_float4(sa[r][c], sa[r][c + 1], sa[r][c + 2], sa[r][c + 3]));
+      wstore4(Ep, o, make_float4(sp[r][c], sp[r][c + 1], sp[r][c + 2], sp[r][c + 3]));
+    }
+    if (offdiag && j0 + r < n && i0 + c < n) {
+      const long long o = eb + (long long)(j0 + r) * Ea.ld + i0 + c;
+      wstore4(Ea, o, make_float4(sa[c][r], sa[c + 1][r], sa[c + 2][r], sa[c + 3][r]));
+      wstore4(Ep, o, make_float4(sp[c][r], sp[c + 1][r], sp[c + 2][r], sp[c + 3][r]));
+    }
+  }
+  const int nterm = (P + 1) * (Q + 1);
+  float* out = partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * nterm;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float v = warp_sum(acc[t]);
+    if (tx == 0) wacc[ty][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int pp = threadIdx.x >> 2, qq = threadIdx.x & 3;
+    if (pp <= P && qq <= Q) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += wacc[w][threadIdx.x];
+      out[pp * (Q + 1) + qq] = v;
+    }
+  }
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int nt,
                                        float* __restrict__ out) {
   __shared__ float sh[32];
@@ -503,6 +755,68 @@ mean_center_kernel(const float* __restrict__ Z, const float* __restrict__ w,
 #pragma unroll
       for (int q = 0; q < kMcGroups; ++q) us += part[q][tx];
       u[(long long)b * d + j] = us * inv;
+    }
+  }
+}
+
+// same, two adjacent columns per thread (8-byte loads, packed bf16x2 stores): d and Zc.ld even
+__global__ void __launch_bounds__(kMcCols * kMcGroups)
+mean_center2_kernel(const float* __restrict__ Z, const float* __restrict__ w,
+                    const float* __restrict__ wdiag, int n, int d, float eps, float* __restrict__ t_out,
+                    float* __restrict__ sw_out, float* __restrict__ mu, float* __restrict__ u, WPtr Zc) {
+  extern __shared__ float shw[];  // n weights
+  __shared__ float sh[32];
+  __shared__ float2 part[kMcGroups][kMcCols];
+  const int b = blockIdx.y;
+  float tl = 0.f, sl = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float wi = w[(long long)b * n + i];
+    shw[i] = wi;
+    sl += wi;
+    tl += wdiag[(long long)b * n + i];
+  }
+  const float t = block_sum(tl, sh);
+  const float sw = block_sum(sl, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { t_out[b] = t; sw_out[b] = sw; }
+  const int tx = threadIdx.x % kMcCols, g = threadIdx.x / kMcCols;
+  const int j = (blockIdx.x * kMcCols + tx) * 2;
+  const bool ok = j < d;
+  const float* z = Z + (long long)b * n * d + j;
+  float2 a = make_float2(0.f, 0.f);
+  if (ok)
+    for (int i = g; i < n; i += kMcGroups) {
+      const float2 v = *reinterpret_cast<const float2*>(z + (long long)i * d);
+      a.x = fmaf(shw[i], v.x, a.x);
+      a.y = fmaf(shw[i], v.y, a.y);
+    }
+  part[g][tx] = a;
+  __syncthreads();
+  a = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < kMcGroups; ++q) { a.x += part[q][tx].x; a.y += part[q][tx].y; }
+  __syncthreads();
+  const float inv = 1.f / (t + eps);
+  const float m0 = a.x * inv, m1 = a.y * inv;
+  float2 ua = make_float2(0.f, 0.f);
+  if (ok) {
+    if (g == 0) *reinterpret_cast<float2*>(mu + (long long)b * d + j) = make_float2(m0, m1);
+    const long long o = (long long)b * Zc.bs + j;
+    for (int i = g; i < n; i += kMcGroups) {
+      const float2 v = *reinterpret_cast<const float2*>(z + (long long)i * d);
+      const float c0 = v.x - m0, c1 = v.y - m1;
+      ua.x = fmaf(c0, shw[i], ua.x);
+      ua.y = fmaf(c1, shw[i], ua.y);
+      wstore2(Zc, o + (long long)i * Zc.ld, c0, c1);
+    }
+  }
+  if (u) {   // kernel-uniform
+    part[g][tx] = ua;
+    __syncthreads();
+    if (g == 0 && ok) {
+      float2 us = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < kMcGroups; ++q) { us.x += part[q][tx].x; us.y += part[q][tx].y; }
+      *reinterpret_cast<float2*>(u + (long long)b * d + j) = make_float2(us.x * inv, us.y * inv);
     }
   }
 }
@@ -960,28 +1274,87 @@ __global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
   a = warp_sum(a);
   if (lane == 0) ds[(long long)b * n + i] = a;
 }
-__global__ void pool_bwd_dG_kernel(const float* __restrict__ dW, long long ldW,
-                                   const float* __restrict__ dw, const float* __restrict__ dt,
-                                   const float* __restrict__ s, const float* __restrict__ deg,
-                                   const float* __restrict__ ds, int n, float eps, int sym,
-                                   float* __restrict__ dG) {
-  const int b = blockIdx.z, i = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const float si = s[(long long)b * n + i], sj = s[(long long)b * n + j];
+// one warp per row: the row's scalars are read once, columns are walked with coalesced accesses
+__global__ void __launch_bounds__(256)
+pool_bwd_dG_kernel(const float* __restrict__ dW, long long ldW, const float* __restrict__ dw,
+                   const float* __restrict__ dt, const float* __restrict__ s,
+                   const float* __restrict__ deg, const float* __restrict__ ds, int n, float eps,
+                   int sym, float* __restrict__ dG) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* sb = s + (long long)b * n;
+  const float* dwb = dw + (long long)b * n;
+  const float* degb = deg + (long long)b * n;
+  const float* dsb = ds + (long long)b * n;
+  const float* dWr = dW + ((long long)b * n + i) * ldW;
+  float* out = dG + ((long long)b * n + i) * n;
+  const float si = sb[i], dwi = dwb[i], dtb = dt[b];
   // s = max(deg,eps)^(-1/2): d s/d deg = -0.5 s^3 where the clamp is inactive (deg >= eps)
-  const float ddeg = (deg[(long long)b * n + i] >= eps) ? -0.5f * si * si * si * ds[(long long)b * n + i] : 0.f;
+  const float ddeg = (degb[i] >= eps) ? -0.5f * si * si * si * dsb[i] : 0.f;
   if (sym) {
     // symmetric graph: return the symmetric part (dG + dG^T)/2 of the reference's gradient, i.e. the
     // gradient with respect to a symmetric matrix (dW is symmetric here; row terms are averaged)
-    const float ddegj = (deg[(long long)b * n + j] >= eps) ? -0.5f * sj * sj * sj * ds[(long long)b * n + j] : 0.f;
-    const float dwf = dW[((long long)b * n + i) * ldW + j] +
-                      0.5f * (dw[(long long)b * n + i] + dw[(long long)b * n + j]) + (i == j ? dt[b] : 0.f);
-    dG[((long long)b * n + i) * n + j] = si * dwf * sj + 0.5f * (ddeg + ddegj);
-    return;
+    for (int j = lane; j < n; j += 32) {
+      const float sj = sb[j];
+      const float ddegj = (degb[j] >= eps) ? -0.5f * sj * sj * sj * dsb[j] : 0.f;
+      const float dwf = dWr[j] + 0.5f * (dwi + dwb[j]) + (i == j ? dtb : 0.f);
+      out[j] = si * dwf * sj + 0.5f * (ddeg + ddegj);
+    }
+  } else {
+    for (int j = lane; j < n; j += 32) {
+      const float dwf = dWr[j] + dwi + (i == j ? dtb : 0.f);
+      out[j] = si * dwf * sb[j] + ddeg;
+    }
   }
-  const float dwf = dW[((long long)b * n + i) * ldW + j] + dw[(long long)b * n + i] + (i == j ? dt[b] : 0.f);
-  dG[((long long)b * n + i) * n + j] = si * dwf * sj + ddeg;
+}
+
+// --------------------------------------------------------- graph alignment loss
+// g[b] = mean(G[b]): one block per image, fixed summation order
+__global__ void __launch_bounds__(1024)
+graph_mean_kernel(const float* __restrict__ G, long long per, float* __restrict__ g) {
+  __shared__ float sh[32];
+  const float* src = G + (long long)blockIdx.x * per;
+  float a = 0.f;
+  for (long long i = threadIdx.x; i < per; i += blockDim.x) a += src[i];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) g[blockIdx.x] = a / (float)per;
+}
+// row i of S = sigmoid(g g^T) against L_ij = [labels_i == labels_j]:
+//   rowloss_i = sum_j (S_ij - L_ij)^2 / B^2,  dg_i = (4/B^2) sum_j (S_ij - L_ij) S_ij (1 - S_ij) g_j
+// (S and L are symmetric, so the (i,j) and (j,i) terms of d/dg_i coincide)
+__global__ void __launch_bounds__(256)
+align_rows_kernel(const float* __restrict__ g, const long long* __restrict__ labels, int batch,
+                  float* __restrict__ rowloss, float* __restrict__ dg) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const float gi = g[i];
+  const long long li = labels[i];
+  float l = 0.f, d = 0.f;
+  for (int j = threadIdx.x; j < batch; j += blockDim.x) {
+    const float gj = g[j];
+    const float s = 1.f / (1.f + __expf(-gi * gj));
+    const float e = s - (labels[j] == li ? 1.f : 0.f);
+    l = fmaf(e, e, l);
+    d = fmaf(e * s * (1.f - s), gj, d);
+  }
+  l = block_sum(l, sh);
+  d = block_sum(d, sh);
+  if (threadIdx.x == 0) {
+    const float inv = 1.f / ((float)batch * (float)batch);
+    rowloss[i] = l * inv;
+    dg[i] = 4.f * d * inv;
+  }
+}
+// dG[b, :, :] = dloss * dg[b] / per
+__global__ void align_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ dloss,
+                                 long long per, float* __restrict__ dG) {
+  const float v = dloss[0] * dg[blockIdx.y] / (float)per;
+  float* dst = dG + (long long)blockIdx.y * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = v;
 }
 
 }  // namespace
@@ -1023,8 +1396,8 @@ void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, 
 void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
                   int symmetric, int batch, int n, float* G, cudaStream_t st) {
   dim3 grid(poly_pairs(n), batch);
-  if (P <= 3 && Q <= 3)
-    gpf_poly_fwd_kernel<3><<<grid, 256, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
+  if (P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31))
+    gpf_poly3_fwd_kernel<<<grid, 256, 0, st>>>(Ra, Rp, (int)ldR, coef, P, Q, symmetric, n, G);
   else
     gpf_poly_fwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(Ra, Rp, ldR, coef, P, Q, symmetric, n, G);
   note_launch();
@@ -1035,9 +1408,9 @@ void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long l
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
                   cudaStream_t st) {
   dim3 grid(poly_pairs(n), batch);
-  if (P <= 3 && Q <= 3)
-    gpf_poly_bwd_kernel<3><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
-                                                 wptr(Ep, prec), partial);
+  if (P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31) && Ea.ld % 4 == 0)
+    gpf_poly3_bwd_kernel<<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
+                                               wptr(Ep, prec), partial);
   else
     gpf_poly_bwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n,
                                                        wptr(Ea, prec), wptr(Ep, prec), partial);
@@ -1060,9 +1433,18 @@ void weight(const float* G, const float* s, int batch, int n, const W& Wn, float
 void mean_center(const float* Z, const float* w, const float* wdiag, int batch, int n, int d,
                  float eps, float* t, float* sw, float* mu, float* u, const W& Zc, int prec,
                  cudaStream_t st) {
-  dim3 grid((d + kMcCols - 1) / kMcCols, batch);
-  mean_center_kernel<<<grid, kMcCols * kMcGroups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
-                                                                           u, wptr(Zc, prec));
+  const bool even = d % 2 == 0 && Zc.ld % 2 == 0 && (reinterpret_cast<uintptr_t>(Z) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(mu) & 7) == 0 && (!u || (reinterpret_cast<uintptr_t>(u) & 7) == 0) &&
+                    (reinterpret_cast<uintptr_t>(Zc.base) & 7) == 0;
+  if (even) {
+    dim3 grid((d / 2 + kMcCols - 1) / kMcCols, batch);
+    mean_center2_kernel<<<grid, kMcCols * kMcGroups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
+                                                                              u, wptr(Zc, prec));
+  } else {
+    dim3 grid((d + kMcCols - 1) / kMcCols, batch);
+    mean_center_kernel<<<grid, kMcCols * kMcGroups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
+                                                                             u, wptr(Zc, prec));
+  }
   note_launch();
 }
 void trace_scales(const float* M, int batch, int d, float eps, int post_mode, float* tr, float* inv,
@@ -1178,8 +1560,8 @@ void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* d
 void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
                  const float* deg, const float* ds, int batch, int n, float eps, int sym, float* dG,
                  cudaStream_t st) {
-  dim3 grid((n + 127) / 128, n, batch);
-  pool_bwd_dG_kernel<<<grid, 128, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, sym, dG);
+  dim3 grid((n + 7) / 8, batch);
+  pool_bwd_dG_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, sym, dG);
   note_launch();
 }
 
@@ -1213,6 +1595,20 @@ void mh_scalars_fwd(const float* tau, int batch, float eps, float* scal, cudaStr
 void mh_dtau(const float* scal, int batch, const float* dotO, const float* dotA, float* dtau,
              cudaStream_t st) {
   mh_dtau_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scal, batch, dotO, dotA, dtau);
+  note_launch();
+}
+void graph_mean(const float* G, int batch, long long per, float* g, cudaStream_t st) {
+  graph_mean_kernel<<<batch, 1024, 0, st>>>(G, per, g);
+  note_launch();
+}
+void align_rows(const float* g, const long long* labels, int batch, float* rowloss, float* dg,
+                cudaStream_t st) {
+  align_rows_kernel<<<batch, 256, 0, st>>>(g, labels, batch, rowloss, dg);
+  note_launch();
+}
+void align_bwd(const float* dg, const float* dloss, int batch, long long per, float* dG, cudaStream_t st) {
+  dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), batch);
+  align_bwd_kernel<<<grid, 256, 0, st>>>(dg, dloss, per, dG);
   note_launch();
 }
 void sum_partials(const float* partial, int nper, int batch, float* out, cudaStream_t st) {

@@ -144,6 +144,13 @@ void mh_dtau(const float* scal, int batch, const float* dotO, const float* dotA,
              cudaStream_t st);
 void sum_partials(const float* partial, int nper, int batch, float* out, cudaStream_t st);
 
+// ---- graph alignment loss (ego_moment_clevit.py:278-316)
+void graph_mean(const float* G, int batch, long long per, float* g, cudaStream_t st);   // g[b] = mean(G[b])
+// rowloss_i = sum_j (sigmoid(g_i g_j) - [l_i == l_j])^2 / B^2 and dg = d(sum rowloss)/dg
+void align_rows(const float* g, const long long* labels, int batch, float* rowloss, float* dg,
+                cudaStream_t st);
+void align_bwd(const float* dg, const float* dloss, int batch, long long per, float* dG, cudaStream_t st);
+
 // ---- pooling backward pieces
 // dmu = -(colsum(dZc) + sw*du/(t+eps))
 void pool_bwd_dmu(const float* dZc, const float* du, const float* sw, const float* t, int batch,

@@ -17,3 +17,16 @@ def install_into(package: str = "src") -> None:
     sys.modules[f"{package}.models.gpf_kernel"] = gpf_kernel
     sys.modules[f"{package}.models.moment_head"] = moment_head
     sys.modules[f"{package}.utils.ops"] = ops
+
+
+def patch_alignment_loss(model_or_class) -> None:
+    """Route `EGOMomentCLEViT._graph_alignment_loss` (ego_moment_clevit.py:278-316, an O(B^2) Python
+    loop of autograd in-place writes) to `functional.graph_alignment_loss` - same value and gradient.
+    Accepts the reference class or an instance of it; nothing else of the class changes."""
+    from . import functional as EF
+    cls = model_or_class if isinstance(model_or_class, type) else type(model_or_class)
+
+    def _graph_alignment_loss(self, fused_graph, labels):
+        return EF.graph_alignment_loss(fused_graph, labels)
+
+    cls._graph_alignment_loss = _graph_alignment_loss

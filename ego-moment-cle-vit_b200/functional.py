@@ -79,6 +79,9 @@ def _p(t):
 
 
 # --------------------------------------------------------------------------- GPF
+_gpf_recompute = os.environ.get("EGM_GPF_RECOMPUTE", "0") == "1"
+
+
 class _GPFFunction(Function):
     @staticmethod
     def forward(ctx, a, p, coef, cosine, eps, symmetric, prec):
@@ -93,12 +96,16 @@ class _GPFFunction(Function):
             Rp = torch.empty(B, N, ldr, device=dev, dtype=torch.float32)
             nrm = torch.empty(2, B, N, device=dev, dtype=torch.float32)
             coef_c = coef.detach().contiguous()
-            ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec), dev)
+            # keep the normalised tokens (GEMM operand planes, 2 x [B,N,D]) for the backward when one
+            # will run; EGM_GPF_RECOMPUTE=1 trades them for a re-normalisation pass in the backward
+            keep = any(ctx.needs_input_grad[:3]) and not _gpf_recompute
+            xn = _ws(L.egm_gpf_state_bytes(B, N, D, prec), dev) if keep else None
+            ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec) if not keep else 16, dev)
             _lib.check(L.egm_gpf_fwd(a.data_ptr(), p.data_ptr(), coef_c.data_ptr(), B, N, D, P, Q,
                                      int(cosine), float(eps), int(symmetric), G.data_ptr(),
                                      Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(),
-                                     prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_gpf_fwd")
-        ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm)
+                                     _p(xn), prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_gpf_fwd")
+        ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm, *([xn] if keep else []))
         ctx.cfg = (int(cosine), float(eps), int(symmetric), prec)
         return G
 
@@ -106,7 +113,8 @@ class _GPFFunction(Function):
     @once_differentiable
     def backward(ctx, dG):
         L = _lib.load()
-        a, p, coef, Ra, Rp, nrm = ctx.saved_tensors
+        a, p, coef, Ra, Rp, nrm = ctx.saved_tensors[:6]
+        xn = ctx.saved_tensors[6] if len(ctx.saved_tensors) > 6 else None
         cosine, eps, symmetric, prec = ctx.cfg
         B, N, D = a.shape
         P, Q = coef.shape[0] - 1, coef.shape[1] - 1
@@ -118,7 +126,7 @@ class _GPFFunction(Function):
             dcoef = torch.empty_like(coef)
             ws = _ws(L.egm_gpf_bwd_workspace(B, N, D, P, Q, prec), dev)
             _lib.check(L.egm_gpf_bwd(dG.data_ptr(), a.data_ptr(), p.data_ptr(), coef.data_ptr(),
-                                     Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(),
+                                     Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(), _p(xn),
                                      B, N, D, P, Q, cosine, eps, symmetric, da.data_ptr(), dp.data_ptr(),
                                      dcoef.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
                        "egm_gpf_bwd")
@@ -623,6 +631,51 @@ def tensor_sketch(x, hashes, signs, csr, sketch_dim):
     x = _require_cuda_f32("x", x, 2)
     off, idx, sgn = csr
     return _SketchFunction.apply(x, hashes, signs, off, idx, sgn, int(sketch_dim))
+
+
+# ---------------------------------------------------------------- alignment loss
+class _AlignLossFunction(Function):
+    @staticmethod
+    def forward(ctx, G, labels):
+        L = _lib.load()
+        B, N, _ = G.shape
+        dev = G.device
+        with torch.cuda.device(dev):
+            buf = torch.empty(3, B, device=dev, dtype=torch.float32)       # g, dg, rowloss
+            loss = torch.empty(1, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_align_fwd(G.data_ptr(), labels.data_ptr(), B, N, buf[0].data_ptr(),
+                                       buf[1].data_ptr(), buf[2].data_ptr(), loss.data_ptr(), _stream(dev)),
+                       "egm_align_fwd")
+        ctx.save_for_backward(buf)
+        ctx.dims = (B, N)
+        return loss.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        L = _lib.load()
+        (buf,) = ctx.saved_tensors
+        B, N = ctx.dims
+        dev = buf.device
+        dloss = dloss.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            dG = torch.empty(B, N, N, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_align_bwd(buf[1].data_ptr(), dloss.data_ptr(), B, N, dG.data_ptr(), _stream(dev)),
+                       "egm_align_bwd")
+        return dG, None
+
+
+def graph_alignment_loss(fused_graph, labels):
+    """mse_loss(sigmoid(g g^T), [labels_i == labels_j]) with g = fused_graph.mean((1, 2))
+    (EGOMomentCLEViT._graph_alignment_loss, ego_moment_clevit.py:278-316) in three small kernels;
+    the reference builds the B x B matrix element by element in Python."""
+    G = _require_cuda_f32("fused_graph", fused_graph, 3)
+    if G.shape[1] != G.shape[2]:
+        raise RuntimeError(f"expected square graphs, got {tuple(G.shape)}")
+    if labels.shape != (G.shape[0],):
+        raise RuntimeError(f"labels shape {tuple(labels.shape)} does not match batch {G.shape[0]}")
+    lab = labels.to(device=G.device, dtype=torch.int64).contiguous()
+    return _AlignLossFunction.apply(G, lab)
 
 
 # ------------------------------------------------------------------ ops helpers

@@ -27,6 +27,7 @@
  *   egm_triu_pack/unpack MomentHead._half_vectorize             src/models/moment_head.py:202-220
  *                        half_vectorize_symmetric               src/utils/ops.py:100-119
  *   egm_sketch_fwd/bwd   TensorSketch.forward/_count_sketch     src/models/moment_head.py:100-133
+ *   egm_align_fwd/bwd    EGOMomentCLEViT._graph_alignment_loss  src/models/ego_moment_clevit.py:278-316
  *   egm_gram_fwd/bwd     cosine_similarity_matrix               src/utils/ops.py:355-381
  *   egm_normalize_graph  normalize_graph                        src/utils/ops.py:238-271
  *   egm_batch_trace      batch_trace                            src/utils/ops.py:316-326
@@ -69,17 +70,20 @@ int egm_prof_read(int i, float* ms, double* flops, int* dims);
 
 /* ---- Graph Polynomial Fusion ------------------------------------------------------------
  * a, p [B,N,D]; coef [(P+1)*(Q+1)] = softplus(alpha) on the device; G [B,N,N].
- * Saved for backward: Ra, Rp [B,N,ldR] with ldR = egm_gpf_ldr(N); nrm_a, nrm_p [B,N]. */
+ * Saved for backward: Ra, Rp [B,N,ldR] with ldR = egm_gpf_ldr(N); nrm_a, nrm_p [B,N]; optionally
+ * xn_state (egm_gpf_state_bytes; opaque: the normalised tokens as GEMM operands). xn_state == NULL
+ * in both calls selects the memory-saving mode: the backward re-normalises the tokens instead. */
 long long egm_gpf_ldr(int N);
+size_t egm_gpf_state_bytes(int B, int N, int D, int prec);
 size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec);
 int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
                 int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
-                float* nrm_p, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+                float* nrm_p, void* xn_state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
 size_t egm_gpf_bwd_workspace(int B, int N, int D, int P, int Q, int prec);
 int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* coef, const float* Ra,
-                const float* Rp, const float* nrm_a, const float* nrm_p, int B, int N, int D, int P,
-                int Q, int cosine, float eps, int symmetric, float* da, float* dp, float* dcoef,
-                int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
+                const float* Rp, const float* nrm_a, const float* nrm_p, const void* xn_state, int B,
+                int N, int D, int P, int Q, int cosine, float eps, int symmetric, float* da, float* dp,
+                float* dcoef, int prec, void* ws, size_t ws_bytes, egm_stream_t stream);
 
 /* ---- graph-weighted second-order pooling ----------------------------------------------------
  * Z [B,N,D] tokens, G [B,N,N] graph (any real matrix) -> M2 [B,D,D], optional u [B,D].
@@ -181,6 +185,15 @@ int egm_sketch_fwd(const float* x, int B, int D, int S, const int* off, const in
                    const float* sgn, float* cs, float* out, egm_stream_t stream);
 int egm_sketch_bwd(const float* dout, const float* cs, int B, int D, int S, const long long* hash,
                    const long long* sign, float* dx, egm_stream_t stream);
+
+/* ---- graph alignment loss (EGOMomentCLEViT._graph_alignment_loss, ego_moment_clevit.py:278-316) ----
+ * g[b] = mean(G[b]); loss = mean_ij (sigmoid(g_i g_j) - [labels_i == labels_j])^2 - the reference fills
+ * the B x B matrix with a Python double loop (B^2 autograd in-place writes). G [B,N,N], labels [B] int64.
+ * Outputs: g [B], dg [B] = d loss / d g (saved for the backward), rowloss [B] scratch, loss [1].
+ * Backward: dG[b,:,:] = dloss[0] * dg[b] / N^2 (dloss: device scalar). */
+int egm_align_fwd(const float* G, const long long* labels, int B, int N, float* g, float* dg,
+                  float* rowloss, float* loss, egm_stream_t stream);
+int egm_align_bwd(const float* dg, const float* dloss, int B, int N, float* dG, egm_stream_t stream);
 
 /* ---- stand-alone matrix helpers (src/utils/ops.py) -------------------------------------------- */
 size_t egm_gram_workspace(int B, int N, int D, int prec);

@@ -414,6 +414,32 @@ def batch_trace(M):
     return np.trace(M, axis1=-2, axis2=-1)
 
 
+# ------------------------------------------------------------- graph alignment loss
+def graph_alignment_loss(fused_graph, labels, dtype=np.float64):
+    """EGOMomentCLEViT._graph_alignment_loss (ego_moment_clevit.py:278-316): g = mean(G) per image,
+    S_ij = sigmoid(g_i g_j) (the reference fills it with a B x B Python loop), loss =
+    mse_loss(S, [labels_i == labels_j]). Returns (loss, g, S)."""
+    G = np.asarray(fused_graph, dtype)
+    labels = np.asarray(labels)
+    label_sim = (labels[None, :] == labels[:, None]).astype(dtype)
+    g = G.mean(axis=(1, 2))
+    S = sigmoid(g[:, None] * g[None, :])
+    return ((S - label_sim) ** 2).mean(), g, S
+
+
+def graph_alignment_loss_backward(fused_graph, labels, dloss=1.0, dtype=np.float64):
+    """d loss / d fused_graph: dS = 2 (S - L)/B^2, d(g g^T) = dS S (1 - S), dg = (X + X^T) g,
+    dG[b] = dg_b / N^2 broadcast over the image's N x N entries."""
+    G = np.asarray(fused_graph, dtype)
+    B, N = G.shape[0], G.shape[1]
+    labels = np.asarray(labels)
+    label_sim = (labels[None, :] == labels[:, None]).astype(dtype)
+    _, g, S = graph_alignment_loss(G, labels, dtype)
+    X = dloss * 2.0 * (S - label_sim) / (B * B) * S * (1.0 - S)
+    dg = (X + X.T) @ g
+    return np.broadcast_to((dg / (N * G.shape[2]))[:, None, None], G.shape).copy()
+
+
 # ------------------------------------------------- whole-path step (bench.py cpu baseline)
 def feature_net_backward(v, params, prefix, dout, train, bn_eps=1e-5):
     """d/d v and d/d weight of Linear -> BatchNorm1d -> GELU (dropout inactive)."""

@@ -190,6 +190,38 @@ def run_new(gk, mh):
 
 
 
+def run_align():
+    """EGOMomentCLEViT._graph_alignment_loss (ego_moment_clevit.py:278-316) of the reference itself:
+    the model module is loaded by file path with the reference's own gpf_kernel / moment_head /
+    classifier_head next to it and a stub in place of the timm backbone module (timm is absent)."""
+    import types
+    pkgname = "egm_ref_src"
+    root = types.ModuleType(pkgname); root.__path__ = []
+    models = types.ModuleType(pkgname + ".models"); models.__path__ = []
+    sys.modules.update({pkgname: root, pkgname + ".models": models})
+    stub = types.ModuleType(pkgname + ".models.cle_vit_backbone")
+    stub.CLEViTDualStream = type("CLEViTDualStream", (torch.nn.Module,), {})
+    sys.modules[pkgname + ".models.cle_vit_backbone"] = stub
+    for name in ("gpf_kernel", "moment_head", "classifier_head", "ego_moment_clevit"):
+        spec = importlib.util.spec_from_file_location(f"{pkgname}.models.{name}",
+                                                      os.path.join(REF, "src", "models", f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkgname}.models.{name}"] = mod
+        spec.loader.exec_module(mod)
+    Model = sys.modules[pkgname + ".models.ego_moment_clevit"].EGOMomentCLEViT
+    g = torch.Generator().manual_seed(99)
+    rec = {}
+    for tag, (B, N, dtype) in {"a": (6, 9, torch.float64), "b": (16, 21, torch.float32)}.items():
+        G = (torch.rand(B, N, N, generator=g) * 2.0).to(dtype).requires_grad_(True)
+        labels = torch.randint(0, 4, (B,), generator=g)
+        loss = Model._graph_alignment_loss(None, G, labels)     # the method never touches `self`
+        (dG,) = torch.autograd.grad(loss * 3.0, G)
+        rec.update({f"{tag}_G": npf(G), f"{tag}_labels": labels.numpy(), f"{tag}_loss": npf(loss),
+                    f"{tag}_dG_x3": npf(dG)})
+    np.savez_compressed(os.path.join(OUT, "align.npz"), **rec)
+    print("align: ok")
+
+
 def main():
     only_new = "--new" in sys.argv
     if not os.path.isdir(REF):
@@ -197,6 +229,9 @@ def main():
     gk = load_ref("ref_gpf_kernel", "src/models/gpf_kernel.py")
     mh = load_ref("ref_moment_head", "src/models/moment_head.py")
     ops = load_ref("ref_ops", "src/utils/ops.py")
+    if "--align" in sys.argv:
+        run_align()
+        return
     if only_new:
         run_new(gk, mh)
         return
@@ -213,6 +248,7 @@ def main():
     run_case(gk, mh, "cfg1_trainbn", B=8, N=197, D=768, P=3, Q=3, K=5, d_out=256, third=False,
              S=0, dtype=torch.float32, full=False, train_bn=True)
     run_new(gk, mh)
+    run_align()
 
 
 if __name__ == "__main__":

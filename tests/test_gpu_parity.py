@@ -707,3 +707,37 @@ def test_sketch_is_trilinear_and_triu_round_trips(pkg, dev):
     assert np.array_equal(npy(v), O.half_vectorize(npy(M)))
     v.backward(torch.ones_like(v))
     assert torch.equal(M.grad, torch.triu(torch.ones(37, 37, device=dev)).expand(3, 37, 37))
+
+
+# ------------------------------------------------------------------ graph alignment loss
+def test_graph_alignment_loss_matches_reference_and_oracle(pkg, dev):
+    """functional.graph_alignment_loss vs the reference's own _graph_alignment_loss (golden) and the
+    oracle at the benchmark's batch size; patch_alignment_loss routes the reference method to it."""
+    EF = pkg.functional
+    rec = golden("align")
+    for tag in ("a", "b"):
+        G = torch.from_numpy(rec[f"{tag}_G"]).float().to(dev).requires_grad_(True)
+        labels = torch.from_numpy(rec[f"{tag}_labels"]).to(dev)
+        loss = EF.graph_alignment_loss(G, labels)
+        (loss * 3.0).backward()
+        assert abs(float(loss) - float(rec[f"{tag}_loss"])) < 2e-6
+        assert rel_err(npy(G.grad), rec[f"{tag}_dG_x3"]) < 1e-4
+    g = torch.Generator().manual_seed(3)
+    B, N = 256, 197
+    G = torch.rand(B, N, N, generator=g)
+    labels = torch.randint(0, 80, (B,), generator=g)
+    ref_loss, _, _ = O.graph_alignment_loss(npy(G), labels.numpy())
+    ref_dG = O.graph_alignment_loss_backward(npy(G), labels.numpy())
+    Gd = G.to(dev).requires_grad_(True)
+    loss = EF.graph_alignment_loss(Gd, labels.to(dev))
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < 1e-5 * max(1.0, ref_loss)
+    assert rel_err(npy(Gd.grad), ref_dG) < 1e-4
+
+    class Model:                      # stands in for the reference class: only the method is replaced
+        def _graph_alignment_loss(self, fused_graph, labels):
+            raise AssertionError("not patched")
+    pkg.patch_alignment_loss(Model)
+    assert abs(float(Model()._graph_alignment_loss(Gd.detach(), labels.to(dev))) - ref_loss) < 1e-5
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        EF.graph_alignment_loss(G, labels)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_argument_errors_are_reported_without_a_gpu(pkg):
     L = pkg._lib.load()
-    rc = L.egm_gpf_fwd(None, None, None, 1, 1, 1, 1, 1, 1, 1e-6, 1, None, None, None, None, None, 1, None, 0, None)
+    rc = L.egm_gpf_fwd(None, None, None, 1, 1, 1, 1, 1, 1, 1e-6, 1, None, None, None, None, None, None, 1, None, 0, None)
     assert rc == -1 and b"null pointer" in L.egm_last_error()
     rc = L.egm_triu_pack(None, 0, 0, None, None)
     assert rc == -1

@@ -92,3 +92,15 @@ def test_ops_helpers():
         O.normalize_graph(rec["graph"], "bogus")
     with pytest.raises(ValueError):
         O.similarity(rec["feats"], "bogus")
+
+
+@pytest.mark.parametrize("tag,tol", [("a", 2e-6), ("b", 2e-6)])
+def test_graph_alignment_loss_matches_reference(tag, tol):
+    """ego_moment_clevit.py:278-316 run by the reference itself. The reference builds its B x B matrix
+    with zeros_like(label_sim.float()), i.e. in float32 whatever the graph's dtype: fp32 tolerances."""
+    rec = golden("align")
+    G, labels = rec[f"{tag}_G"], rec[f"{tag}_labels"]
+    loss, g, S = O.graph_alignment_loss(G, labels)
+    assert abs(loss - float(rec[f"{tag}_loss"])) < tol * max(1.0, abs(loss))
+    dG = O.graph_alignment_loss_backward(G, labels, dloss=3.0)
+    assert rel_err(dG, rec[f"{tag}_dG_x3"]) < max(tol, 1e-9) * 10
