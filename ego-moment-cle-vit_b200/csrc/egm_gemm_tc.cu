@@ -326,16 +326,20 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
       stage_planes(buf, lane, o, p.X_lo != nullptr);
       __syncwarp();
       const int j = col0 + lane;
-#pragma unroll 4
+      const int rows = min(32, p.M - row0);
+      // packed offset of (i, j) is base_i + j with base_{i+1} = base_i + N - i - 1: one add per row
+      long long base = (long long)b * p.ldX + (long long)row0 * p.N - (long long)row0 * (row0 - 1) / 2 - row0;
+      const uint32_t lane_off = (lane & 7) * 2;
+      const uint32_t lane_sw = lane >> 3;
+      const bool has_lo = p.X_lo != nullptr;
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const int i = row0 + r;
-        if (i >= p.M) break;  // warp-uniform
-        if (j >= i && j < p.N) {
-          const uint32_t off = r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4) + (lane & 7) * 2;
-          const long long idx = (long long)b * p.ldX + (long long)i * p.N - (long long)i * (i - 1) / 2 + (j - i);
-          p.X_hi[idx] = __ushort_as_bfloat16(ptx::lds16(buf + off));
-          if (p.X_lo) p.X_lo[idx] = __ushort_as_bfloat16(ptx::lds16(buf + 2048 + off));
+        if (r < rows && j >= row0 + r && j < p.N) {
+          const uint32_t off = r * 64 + ((lane_sw ^ ((r >> 1) & 3)) << 4) + lane_off;
+          p.X_hi[base + j] = __ushort_as_bfloat16(ptx::lds16(buf + off));
+          if (has_lo) p.X_lo[base + j] = __ushort_as_bfloat16(ptx::lds16(buf + 2048 + off));
         }
+        base += p.N - (row0 + r) - 1;
       }
     }
     if (p.Cf) {
