@@ -741,3 +741,50 @@ def test_graph_alignment_loss_matches_reference_and_oracle(pkg, dev):
     assert abs(float(Model()._graph_alignment_loss(Gd.detach(), labels.to(dev))) - ref_loss) < 1e-5
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         EF.graph_alignment_loss(G, labels)
+
+
+# ------------------------------------------------------------------------ CUDA graph capture
+def test_whole_step_is_cuda_graph_capturable(pkg, dev):
+    """The library never allocates or synchronises and takes the caller's stream, so a full
+    GPF -> MomentHead forward + backward can be captured once and replayed on new inputs
+    (what a launch-bound small-batch loop needs)."""
+    EF = pkg.functional
+    B, N, D = 4, 50, 128
+    torch.manual_seed(0)
+    gpf = pkg.GraphPolynomialFusion(3, 3).to(dev)
+    head = pkg.MomentHead(D, 32, use_third_order=True, isqrt_iterations=5, sketch_dim=256).to(dev).eval()
+    params = list(gpf.parameters()) + list(head.parameters())
+    a = torch.zeros(B, N, D, device=dev, requires_grad=True)
+    p = torch.zeros(B, N, D, device=dev, requires_grad=True)
+    dout = torch.randn(B, 32, device=dev)
+    xs = [tuple(t.to(dev) for t in make_inputs(B, N, D, seed=s)) for s in (1, 2, 3)]
+
+    def step():
+        for t in params + [a, p]:
+            t.grad = None
+        out = head(a, gpf(a, p))
+        (out * dout).sum().backward()
+        return out
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                 # warm-up off the capture (lazy init, CSR tables)
+        with torch.no_grad():
+            a.copy_(xs[0][0]); p.copy_(xs[0][1])
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_g = step()
+    grads_g = [a.grad, p.grad, gpf.alpha_coeffs.grad, head.second_net[0].weight.grad]
+    for xa, xp in xs[1:]:
+        with torch.no_grad():
+            a.copy_(xa); p.copy_(xp)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [out_g.clone()] + [g.clone() for g in grads_g]
+        out_e = step()                              # eager, same inputs
+        want = [out_e, a.grad, p.grad, gpf.alpha_coeffs.grad, head.second_net[0].weight.grad]
+        for x, y in zip(got, want):
+            assert torch.equal(x, y)                # deterministic kernels: bit-identical
