@@ -55,6 +55,7 @@ struct alignas(64) TcParams {
   CUtensorMap tmC[3];    // TMA-store maps: C_hi, C_lo (bf16, 64B swizzle), C_f32 (128B swizzle)
   CUtensorMap tmC2[2];   // TMA-store maps of the secondary plane output
   int tma_cp, tma_cf, tma_c2;  // which outputs leave through TMA stores
+  int epi_split;         // hi and lo plane stores of a chunk as separate bulk groups
   int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
@@ -193,52 +194,81 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   return r;
 }
 
-// one lane's row of a 32 x 32 chunk -> bf16 hi/lo staging slot (rows of 64 B, 64B swizzle)
-__device__ __forceinline__ void stage_planes(uint32_t buf, int lane, const float (&o)[32], bool has_lo) {
+// one lane's row of a 32 x 32 chunk -> packed bf16 hi words and the fp32 residuals' packed lo words
+__device__ __forceinline__ void split_row(const float (&o)[32], uint32_t (&hw)[16], uint32_t (&lw)[16],
+                                          bool has_lo) {
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    hw[w] = cvt_bf16x2(o[2 * w + 1], o[2 * w]);
+    if (has_lo)
+      lw[w] = cvt_bf16x2(o[2 * w + 1] - __uint_as_float(hw[w] & 0xFFFF0000u),
+                         o[2 * w] - __uint_as_float(hw[w] << 16));
+  }
+}
+// 16 packed words of one lane's row -> a 2 KiB plane staging area (rows of 64 B, 64B swizzle)
+__device__ __forceinline__ void stage_words(uint32_t buf, int lane, const uint32_t (&w)[16]) {
   const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t hw[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w) hw[w] = cvt_bf16x2(o[j * 8 + 2 * w + 1], o[j * 8 + 2 * w]);
-    const uint32_t off = lane * 64 + ((j ^ sw) << 4);
-    ptx::sts128(buf + off, hw[0], hw[1], hw[2], hw[3]);
-    if (has_lo) {
-      uint32_t lw[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w)
-        lw[w] = cvt_bf16x2(o[j * 8 + 2 * w + 1] - __uint_as_float(hw[w] & 0xFFFF0000u),
-                           o[j * 8 + 2 * w] - __uint_as_float(hw[w] << 16));
-      ptx::sts128(buf + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
-    }
-  }
+  for (int j = 0; j < 4; ++j)
+    ptx::sts128(buf + lane * 64 + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+// one lane's row of a 32 x 32 chunk -> bf16 hi/lo staging slot (hi at +0, lo at +2048)
+__device__ __forceinline__ void stage_planes(uint32_t buf, int lane, const float (&o)[32], bool has_lo) {
+  uint32_t hw[16], lw[16];
+  split_row(o, hw, lw, has_lo);
+  stage_words(buf, lane, hw);
+  if (has_lo) stage_words(buf + 2048, lane, lw);
 }
 
 // Plane output of one chunk: TMA store through the warp's staging slot when the layout allows
 // it (full-line writes, no LSU traffic, ragged edges clipped by the tensor map), else scalar.
+// The slot is two 2 KiB halves and every half-store is its own bulk group, so a half is rewritten
+// only after the store issued two groups earlier has read it (wait_group.read 1): with hi + lo
+// planes the halves are the two planes, with a single plane they alternate (`half_slot`).
 __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, const CUtensorMap* tmh,
                                              const CUtensorMap* tml, __nv_bfloat16* hi,
                                              __nv_bfloat16* lo, long long ld, long long bs, int b,
                                              int row, int row0, int col0, int ncols, bool row_ok,
-                                             int lane, uint32_t buf, int& half_slot) {
+                                             int lane, uint32_t buf, int& half_slot, bool split) {
   if (tma) {
-    // hi + lo fill the 4 KiB slot; a hi-only store (single-pass mode) needs half of it, so two
-    // stores can be in flight and the wait below almost never blocks
-    if (lo) {
-      if (lane == 0) ptx::bulk_wait_read<0>();   // the store that used this slot has drained
-    } else {
-      buf += half_slot * 2048;
-      half_slot ^= 1;
-      if (lane == 0) ptx::bulk_wait_read<1>();
+    uint32_t hw[16], lw[16];
+    split_row(o, hw, lw, lo != nullptr);
+    if (lo && !split) {
+      // one bulk group per chunk: the whole slot must have drained
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
+      stage_words(buf, lane, hw);
+      stage_words(buf + 2048, lane, lw);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_3d(tmh, buf, col0, row0, b);
+        ptx::tma_store_3d(tml, buf + 2048, col0, row0, b);
+        ptx::bulk_commit();
+      }
+      return;
     }
+    const uint32_t hbuf = lo ? buf : buf + half_slot * 2048;
+    if (!lo) half_slot ^= 1;
+    if (lane == 0) ptx::bulk_wait_read<1>();   // the store that last used this half has drained
     __syncwarp();
-    stage_planes(buf, lane, o, lo != nullptr);
+    stage_words(hbuf, lane, hw);
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      ptx::tma_store_3d(tmh, buf, col0, row0, b);
-      if (lo) ptx::tma_store_3d(tml, buf + 2048, col0, row0, b);
+      ptx::tma_store_3d(tmh, hbuf, col0, row0, b);
       ptx::bulk_commit();
+    }
+    if (lo) {
+      if (lane == 0) ptx::bulk_wait_read<1>();
+      __syncwarp();
+      stage_words(buf + 2048, lane, lw);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_3d(tml, buf + 2048, col0, row0, b);
+        ptx::bulk_commit();
+      }
     }
   } else if (row_ok) {
     __nv_bfloat16* ch = hi + b * bs + (long long)row * ld + col0;
@@ -307,7 +337,7 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
     }
     if (p.Cp_hi)
       store_planes(o, p.tma_cp != 0, &p.tmC[0], &p.tmC[1], p.Cp_hi, p.Cp_lo, p.ldCp, p.bsCp, b, row, row0,
-                   col0, p.N, row_ok, lane, buf, half_slot);
+                   col0, p.N, row_ok, lane, buf, half_slot, p.epi_split != 0);
     if (p.C2_hi) {
       float o2[32];
 #pragma unroll
@@ -318,7 +348,7 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
           if (j == lane) o2[j] += p.c2_eye;
       }
       store_planes(o2, p.tma_c2 != 0, &p.tmC2[0], &p.tmC2[1], p.C2_hi, p.C2_lo, p.ldC2, p.bsC2, b, row,
-                   row0, col0, p.N, row_ok, lane, buf, half_slot);
+                   row0, col0, p.N, row_ok, lane, buf, half_slot, p.epi_split != 0);
     }
     if (p.X_hi) {
       // packed upper triangle: stage the chunk, then every row leaves as one contiguous run
@@ -966,6 +996,18 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// hi and lo plane stores of a chunk as one bulk group or two. Two groups keep a store in flight while
+// the other half is restaged: -2 % on the long-K Newton-Schulz products (mainloop-bound, the epilogue
+// only has to stay out of the way), +5 % on short-K products whose time IS the epilogue (measured A/B
+// on one box). EGM_EPI_SPLIT=0/1 forces either.
+int epi_split_for(int total_k) {
+  static int forced = []() {
+    const char* e = getenv("EGM_EPI_SPLIT");
+    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  return forced >= 0 ? forced : (total_k >= 512 ? 1 : 0);
+}
+
 // EGM_GEMM_CTAS=1 selects the single-CTA kernel (kept for A/B measurements); default is the pair.
 int tc_ctas() {
   static int v = []() {
@@ -1068,6 +1110,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
       if (!make_plane_map(&p.tm[t][3], B.p1, B, ab_batch, b_rows)) return cudaErrorInvalidValue;
     }
   }
+  p.epi_split = epi_split_for(g.t[0].K + (g.nterms > 1 ? g.t[1].K : 0));
   if (g.split_k > 1) {
     // K-slices of one product; slice s writes partial sums to output batch index s
     const int nkb = (g.t[0].K + BK - 1) / BK;
