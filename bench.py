@@ -12,7 +12,8 @@ batch. Weak scaling: the per-GPU batch is fixed, `value` is the whole-job images
   value      inputs already resident in HBM (two rotating 310 MB input sets > 126 MB L2)
   e2e        same step through the public nn.Module API with HOST (pinned) token buffers:
              H2D copy of both token tensors (double-buffered on a copy stream) + D2H read of the
-             loss of every step, all inside the timed region
+             loss of every step, all inside the timed region. Timed FIRST, `value` right after it:
+             under the 1 kW power cap the same K steps read ~3 % slower a few seconds later
   roofline   the dominant kernel (tcgen05 GEMM engine, Newton-Schulz chain), timed live with
              CUDA events inside the timed steps, against MEASURED_PEAKS.json
   cpu_baseline  the numpy oracle port of the reference's algorithm on the host cores (bounded

@@ -5,22 +5,28 @@
 // :292-293 pooling products, src/models/gpf_kernel.py:88 Gram) and the elementwise passes
 // around them (`3*I - ZY`, `0.5 *`, `/ sqrt(trace)`), which are folded into the epilogue.
 //
-// Shape of the kernel (one persistent CTA per SM, 192 threads):
+// Shape of the kernel (one persistent CTA per SM, 320 threads; default: CTA pairs, see below):
 //   warp 0      TMA producer: cp.async.bulk.tensor 3-D boxes {64 x rows x 1 image} of the
 //               bf16 operand planes into 128B-swizzled shared memory, mbarrier-signalled
-//   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::f16 (128 x 256 x 16 per
-//               instruction) into one of two 256-column fp32 accumulators in TMEM
-//   warps 2..5  epilogue: tcgen05.ld the finished accumulator (32 lanes x 32 columns per
-//               load), apply  alpha*acc + beta*I + gamma*E, split to bf16 hi/lo planes and/or
-//               write fp32, while the MMA warp is already filling the other accumulator
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::f16 (128 x 256 x 16, or 256 x 256 x 16
+//               over a CTA pair) into one of two 256-column fp32 accumulators in TMEM
+//   warps 2..9  epilogue, two per TMEM lane quarter (each takes half of the columns): tcgen05.ld the
+//               finished accumulator (32 lanes x 32 columns per load, the next load in flight),
+//               apply  alpha*acc + beta*I + gamma*E, split to bf16 hi/lo planes and/or write fp32
+//               through swizzled staging + TMA stores, while the MMA warp fills the other accumulator
 //
 // fp32 fidelity ("bf16x3"): every fp32 operand x is carried as two bf16 planes
 // hi = bf16(x), lo = bf16(x - hi).  A*B ~= Ah*Bh + Ah*Bl + Al*Bh  (3 MMAs, fp32 accumulate,
 // relative error ~1e-5).  The single-pass mode issues Ah*Bh only.
 //
 // Up to two products are accumulated into the same TMEM tile (C = A0*B0 + A1*B1), which
-// is what the Newton-Schulz backward needs (e.g. dY = dY'*T^T + Z^T*dP) without a
+// is what the Newton-Schulz backward needs (e.g. Y'_{k+1} = Y'_k*T_k + Y_k*T'_k) without a
 // read-modify-write epilogue.
+//
+// Symmetric matrices (the whole Newton-Schulz chain when the graph is symmetric) are kept as their
+// upper 256 x 256 blocks only: a `sym_out` product computes just the tiles that touch those blocks,
+// and a `sym` operand whose block is absent is loaded from the mirrored block with the operand's
+// major-ness (K-major <-> MN-major) flipped in the UMMA descriptors - see sym_a_mn / sym_b_mn.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
