@@ -66,8 +66,32 @@ def _require_cuda_f32(name: str, t: torch.Tensor, ndim: int) -> torch.Tensor:
     return t.contiguous()
 
 
+# EGM_POISON=1 (tests): every buffer this module allocates - outputs, saved state, scratch - starts as
+# 0xFF bytes (NaN in fp32 and bf16), so a kernel that reads memory nobody wrote cannot pass by luck.
+_poison = os.environ.get("EGM_POISON", "0") == "1"
+
+
+def set_poison(on: bool) -> None:
+    global _poison
+    _poison = bool(on)
+
+
+def _empty(*size, **kw) -> torch.Tensor:
+    t = torch.empty(*size, **kw)
+    if _poison:
+        t.view(torch.uint8).fill_(0xFF) if t.dtype != torch.uint8 else t.fill_(0xFF)
+    return t
+
+
+def _empty_like(x: torch.Tensor) -> torch.Tensor:
+    t = torch.empty_like(x)
+    if _poison:
+        t.view(torch.uint8).fill_(0xFF)
+    return t
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return _empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
 def _stream(device) -> int:
@@ -91,10 +115,10 @@ class _GPFFunction(Function):
         dev = a.device
         ldr = L.egm_gpf_ldr(N)
         with torch.cuda.device(dev):
-            G = torch.empty(B, N, N, device=dev, dtype=torch.float32)
-            Ra = torch.empty(B, N, ldr, device=dev, dtype=torch.float32)
-            Rp = torch.empty(B, N, ldr, device=dev, dtype=torch.float32)
-            nrm = torch.empty(2, B, N, device=dev, dtype=torch.float32)
+            G = _empty(B, N, N, device=dev, dtype=torch.float32)
+            Ra = _empty(B, N, ldr, device=dev, dtype=torch.float32)
+            Rp = _empty(B, N, ldr, device=dev, dtype=torch.float32)
+            nrm = _empty(2, B, N, device=dev, dtype=torch.float32)
             coef_c = coef.detach().contiguous()
             # keep the normalised tokens (GEMM operand planes, 2 x [B,N,D]) for the backward when one
             # will run; EGM_GPF_RECOMPUTE=1 trades them for a re-normalisation pass in the backward
@@ -121,9 +145,9 @@ class _GPFFunction(Function):
         dev = a.device
         dG = dG.contiguous()
         with torch.cuda.device(dev):
-            da = torch.empty_like(a)
-            dp = torch.empty_like(p)
-            dcoef = torch.empty_like(coef)
+            da = _empty_like(a)
+            dp = _empty_like(p)
+            dcoef = _empty_like(coef)
             ws = _ws(L.egm_gpf_bwd_workspace(B, N, D, P, Q, prec), dev)
             _lib.check(L.egm_gpf_bwd(dG.data_ptr(), a.data_ptr(), p.data_ptr(), coef.data_ptr(),
                                      Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(), _p(xn),
@@ -157,10 +181,10 @@ class _PoolFunction(Function):
         B, N, D = Z.shape
         dev = Z.device
         with torch.cuda.device(dev):
-            M2 = torch.empty(B, D, D, device=dev, dtype=torch.float32)
-            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
-            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
-            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
+            M2 = _empty(B, D, D, device=dev, dtype=torch.float32)
+            u = _empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = _empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = _empty(B, D, device=dev, dtype=torch.float32)
             state = _ws(L.egm_pool_state_bytes(B, N, D, prec), dev)
             ws = _ws(L.egm_pool_fwd_workspace(B, N, D, prec), dev)
             _lib.check(L.egm_pool_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, float(eps), M2.data_ptr(),
@@ -188,8 +212,8 @@ class _PoolFunction(Function):
             dM2 = dM2.contiguous()
             if du is not None:
                 du = du.contiguous()
-            dZ = torch.empty_like(Z)
-            dG = torch.empty_like(G)
+            dZ = _empty_like(Z)
+            dG = _empty_like(G)
             ws = _ws(L.egm_pool_bwd_workspace(B, N, D, prec), dev)
             _lib.check(L.egm_pool_bwd(dM2.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(), _p(u),
                                       vecs.data_ptr(), mu.data_ptr(), state.data_ptr(), B, N, D, eps,
@@ -207,11 +231,11 @@ class _MomentLowRankFunction(Function):
         B, N, D = Z.shape
         dev = Z.device
         with torch.cuda.device(dev):
-            O = torch.empty(B, D, D, device=dev, dtype=torch.float32)
-            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
-            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
-            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
-            scal = torch.empty(5, B, device=dev, dtype=torch.float32)
+            O = _empty(B, D, D, device=dev, dtype=torch.float32)
+            u = _empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = _empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = _empty(B, D, device=dev, dtype=torch.float32)
+            scal = _empty(5, B, device=dev, dtype=torch.float32)
             state = _ws(L.egm_mlr_state_bytes(B, N, D, iters, prec), dev)
             ws = _ws(L.egm_mlr_fwd_workspace(B, N, D, iters, prec), dev)
             _lib.check(L.egm_mlr_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps),
@@ -240,8 +264,8 @@ class _MomentLowRankFunction(Function):
             dO = dO.contiguous()
             if du is not None:
                 du = du.contiguous()
-            dZ = torch.empty_like(Z)
-            dG = torch.empty_like(G)
+            dZ = _empty_like(Z)
+            dG = _empty_like(G)
             ws = _ws(L.egm_mlr_bwd_workspace(B, N, D, iters, prec), dev)
             _lib.check(L.egm_mlr_bwd(dO.data_ptr(), None, None, _p(du), Z.data_ptr(), G.data_ptr(), O.data_ptr(), _p(u),
                                      vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
@@ -262,13 +286,13 @@ class _MomentHeadLinearFunction(Function):
         n_out, K = weight.shape
         dev = Z.device
         with torch.cuda.device(dev):
-            y = torch.empty(B, n_out, device=dev, dtype=torch.float32)
-            u = torch.empty(B, D, device=dev, dtype=torch.float32) if want_u else None
-            vecs = torch.empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
-            mu = torch.empty(B, D, device=dev, dtype=torch.float32)
+            y = _empty(B, n_out, device=dev, dtype=torch.float32)
+            u = _empty(B, D, device=dev, dtype=torch.float32) if want_u else None
+            vecs = _empty(B * (4 * N + 2), device=dev, dtype=torch.float32)
+            mu = _empty(B, D, device=dev, dtype=torch.float32)
             lin_state = _ws(L.egm_linear_state_bytes(B, n_out, K, prec), dev)
             if lowrank:
-                scal = torch.empty(5, B, device=dev, dtype=torch.float32)
+                scal = _empty(5, B, device=dev, dtype=torch.float32)
                 state = _ws(L.egm_mlr_state_bytes(B, N, D, iters, prec), dev)
                 ws = _ws(L.egm_mlr_fwd_workspace(B, N, D, iters, prec), dev)
                 _lib.check(L.egm_mlr_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps), None,
@@ -276,7 +300,7 @@ class _MomentHeadLinearFunction(Function):
                                          scal.data_ptr(), state.data_ptr(), prec, ws.data_ptr(), ws.numel(),
                                          _stream(dev)), "egm_mlr_fwd")
             else:
-                scal = torch.empty(3, B, device=dev, dtype=torch.float32)
+                scal = _empty(3, B, device=dev, dtype=torch.float32)
                 state = _ws(L.egm_mhd_state_bytes(B, N, D, iters, prec), dev)
                 ws = _ws(L.egm_mhd_fwd_workspace(B, N, D, iters, prec), dev)
                 _lib.check(L.egm_mhd_fwd(Z.data_ptr(), G.data_ptr(), B, N, D, int(iters), float(eps), int(flags),
@@ -315,18 +339,18 @@ class _MomentHeadLinearFunction(Function):
             dy = dy.contiguous()
             if du is not None:
                 du = du.contiguous()
-            dv = torch.empty(B, K, device=dev, dtype=torch.float32)
-            dw = torch.empty(n_out, K, device=dev, dtype=torch.float32) if need_w else None
-            db = torch.empty(n_out, device=dev, dtype=torch.float32) if need_b else None
+            dv = _empty(B, K, device=dev, dtype=torch.float32)
+            dw = _empty(n_out, K, device=dev, dtype=torch.float32) if need_w else None
+            db = _empty(n_out, device=dev, dtype=torch.float32) if need_b else None
             ws = _ws(L.egm_linear_bwd_workspace(B, n_out, K, prec), dev)
             _lib.check(L.egm_linear_bwd(dy.data_ptr(), lin_state.data_ptr(), B, n_out, K, dv.data_ptr(),
                                         _p(dw), _p(db), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
                        "egm_linear_bwd")
-            dot = torch.empty(B, device=dev, dtype=torch.float32)   # <dO, O> = <dy, y - bias>
+            dot = _empty(B, device=dev, dtype=torch.float32)   # <dO, O> = <dy, y - bias>
             _lib.check(L.egm_rowdot_bias(dy.data_ptr(), y.data_ptr(), _p(bias), B, n_out, dot.data_ptr(),
                                          _stream(dev)), "egm_rowdot_bias")
-            dZ = torch.empty_like(Z)
-            dG = torch.empty_like(G)
+            dZ = _empty_like(Z)
+            dG = _empty_like(G)
             if lowrank:
                 ws = _ws(L.egm_mlr_bwd_workspace(B, N, D, iters, prec), dev)
                 _lib.check(L.egm_mlr_bwd(None, dv.data_ptr(), dot.data_ptr(), _p(du), Z.data_ptr(), G.data_ptr(),
@@ -449,8 +473,8 @@ class _NSFunction(Function):
         B, D, _ = M.shape
         dev = M.device
         with torch.cuda.device(dev):
-            O = torch.empty_like(M)
-            scal = torch.empty(3, B, device=dev, dtype=torch.float32)
+            O = _empty_like(M)
+            scal = _empty(3, B, device=dev, dtype=torch.float32)
             state = _ws(L.egm_ns_state_bytes(B, D, iters, prec), dev)
             ws = _ws(L.egm_ns_fwd_workspace(B, D, iters, prec), dev)
             _lib.check(L.egm_ns_fwd(M.data_ptr(), B, D, int(iters), float(eps), int(post_mode),
@@ -470,7 +494,7 @@ class _NSFunction(Function):
         dev = M.device
         dO = dO.contiguous()
         with torch.cuda.device(dev):
-            dM = torch.empty_like(M)
+            dM = _empty_like(M)
             ws = _ws(L.egm_ns_bwd_workspace(B, D, iters, prec), dev)
             _lib.check(L.egm_ns_bwd(dO.data_ptr(), O.data_ptr(), M.data_ptr(), scal.data_ptr(),
                                     state.data_ptr(), B, D, iters, eps, post_mode, dM.data_ptr(), prec,
@@ -498,7 +522,7 @@ class _LinearFunction(Function):
         N = weight.shape[0]
         dev = x.device
         with torch.cuda.device(dev):
-            y = torch.empty(M, N, device=dev, dtype=torch.float32)
+            y = _empty(M, N, device=dev, dtype=torch.float32)
             state = _ws(L.egm_linear_state_bytes(M, N, K, prec), dev)
             ws = _ws(L.egm_linear_fwd_workspace(M, N, K, prec), dev)
             _lib.check(L.egm_linear_fwd(x.data_ptr(), weight.data_ptr(), _p(bias), M, N, K, y.data_ptr(),
@@ -518,9 +542,9 @@ class _LinearFunction(Function):
         dy = dy.contiguous()
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
         with torch.cuda.device(dev):
-            dx = torch.empty(M, K, device=dev, dtype=torch.float32) if need_x else None
-            dw = torch.empty(N, K, device=dev, dtype=torch.float32) if need_w else None
-            db = torch.empty(N, device=dev, dtype=torch.float32) if need_b else None
+            dx = _empty(M, K, device=dev, dtype=torch.float32) if need_x else None
+            dw = _empty(N, K, device=dev, dtype=torch.float32) if need_w else None
+            db = _empty(N, device=dev, dtype=torch.float32) if need_b else None
             ws = _ws(L.egm_linear_bwd_workspace(M, N, K, prec), dev)
             _lib.check(L.egm_linear_bwd(dy.data_ptr(), state.data_ptr(), M, N, K, _p(dx), _p(dw), _p(db), prec,
                                         ws.data_ptr(), ws.numel(), _stream(dev)), "egm_linear_bwd")
@@ -549,7 +573,7 @@ class _TriuFunction(Function):
         B, D, _ = O.shape
         dev = O.device
         with torch.cuda.device(dev):
-            v = torch.empty(B, D * (D + 1) // 2, device=dev, dtype=torch.float32)
+            v = _empty(B, D * (D + 1) // 2, device=dev, dtype=torch.float32)
             _lib.check(L.egm_triu_pack(O.data_ptr(), B, D, v.data_ptr(), _stream(dev)), "egm_triu_pack")
         ctx.dims = (B, D)
         return v
@@ -562,7 +586,7 @@ class _TriuFunction(Function):
         dev = dv.device
         dv = dv.contiguous()
         with torch.cuda.device(dev):
-            dO = torch.empty(B, D, D, device=dev, dtype=torch.float32)
+            dO = _empty(B, D, D, device=dev, dtype=torch.float32)
             _lib.check(L.egm_triu_unpack(dv.data_ptr(), B, D, dO.data_ptr(), _stream(dev)),
                        "egm_triu_unpack")
         return dO
@@ -602,8 +626,8 @@ class _SketchFunction(Function):
         B, D = x.shape
         dev = x.device
         with torch.cuda.device(dev):
-            cs = torch.empty(3, B, S, device=dev, dtype=torch.float32)
-            out = torch.empty(B, S, device=dev, dtype=torch.float32)
+            cs = _empty(3, B, S, device=dev, dtype=torch.float32)
+            out = _empty(B, S, device=dev, dtype=torch.float32)
             _lib.check(L.egm_sketch_fwd(x.data_ptr(), B, D, S, off.data_ptr(), idx.data_ptr(),
                                         sgn.data_ptr(), cs.data_ptr(), out.data_ptr(), _stream(dev)),
                        "egm_sketch_fwd")
@@ -620,7 +644,7 @@ class _SketchFunction(Function):
         dev = dout.device
         dout = dout.contiguous()
         with torch.cuda.device(dev):
-            dx = torch.empty(B, D, device=dev, dtype=torch.float32)
+            dx = _empty(B, D, device=dev, dtype=torch.float32)
             _lib.check(L.egm_sketch_bwd(dout.data_ptr(), cs.data_ptr(), B, D, S, hashes.data_ptr(),
                                         signs.data_ptr(), dx.data_ptr(), _stream(dev)), "egm_sketch_bwd")
         return dx, None, None, None, None, None, None
@@ -641,8 +665,8 @@ class _AlignLossFunction(Function):
         B, N, _ = G.shape
         dev = G.device
         with torch.cuda.device(dev):
-            buf = torch.empty(3, B, device=dev, dtype=torch.float32)       # g, dg, rowloss
-            loss = torch.empty(1, device=dev, dtype=torch.float32)
+            buf = _empty(3, B, device=dev, dtype=torch.float32)       # g, dg, rowloss
+            loss = _empty(1, device=dev, dtype=torch.float32)
             _lib.check(L.egm_align_fwd(G.data_ptr(), labels.data_ptr(), B, N, buf[0].data_ptr(),
                                        buf[1].data_ptr(), buf[2].data_ptr(), loss.data_ptr(), _stream(dev)),
                        "egm_align_fwd")
@@ -659,7 +683,7 @@ class _AlignLossFunction(Function):
         dev = buf.device
         dloss = dloss.to(torch.float32).reshape(1).contiguous()
         with torch.cuda.device(dev):
-            dG = torch.empty(B, N, N, device=dev, dtype=torch.float32)
+            dG = _empty(B, N, N, device=dev, dtype=torch.float32)
             _lib.check(L.egm_align_bwd(buf[1].data_ptr(), dloss.data_ptr(), B, N, dG.data_ptr(), _stream(dev)),
                        "egm_align_bwd")
         return dG, None
@@ -686,8 +710,8 @@ class _GramFunction(Function):
         B, N, D = x.shape
         dev = x.device
         with torch.cuda.device(dev):
-            R = torch.empty(B, N, N, device=dev, dtype=torch.float32)
-            nrm = torch.empty(B, N, device=dev, dtype=torch.float32)
+            R = _empty(B, N, N, device=dev, dtype=torch.float32)
+            nrm = _empty(B, N, device=dev, dtype=torch.float32)
             ws = _ws(L.egm_gram_workspace(B, N, D, prec), dev)
             _lib.check(L.egm_gram_fwd(x.data_ptr(), B, N, D, int(cosine), float(eps), R.data_ptr(),
                                       nrm.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
@@ -706,7 +730,7 @@ class _GramFunction(Function):
         dev = x.device
         dR = dR.contiguous()
         with torch.cuda.device(dev):
-            dx = torch.empty_like(x)
+            dx = _empty_like(x)
             ws = _ws(L.egm_gram_workspace(B, N, D, prec), dev)
             _lib.check(L.egm_gram_bwd(dR.data_ptr(), x.data_ptr(), nrm.data_ptr(), B, N, D, cosine, eps,
                                       dx.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
@@ -727,8 +751,8 @@ def normalize_graph(graph, method: int, eps: float):
     B, N, _ = G.shape
     dev = G.device
     with torch.cuda.device(dev):
-        out = torch.empty_like(G)
-        deg = torch.empty(B, N, device=dev, dtype=torch.float32)
+        out = _empty_like(G)
+        deg = _empty(B, N, device=dev, dtype=torch.float32)
         _lib.check(L.egm_normalize_graph(G.data_ptr(), B, N, int(method), float(eps), out.data_ptr(),
                                          deg.data_ptr(), _stream(dev)), "egm_normalize_graph")
     return out, deg
@@ -740,7 +764,7 @@ def batch_trace(matrices):
     B, D, _ = M.shape
     dev = M.device
     with torch.cuda.device(dev):
-        tr = torch.empty(B, device=dev, dtype=torch.float32)
+        tr = _empty(B, device=dev, dtype=torch.float32)
         _lib.check(L.egm_batch_trace(M.data_ptr(), B, D, tr.data_ptr(), _stream(dev)), "egm_batch_trace")
     return tr
 
@@ -756,7 +780,7 @@ def bmm(A, B, *, trans_a=False, trans_b=False, alpha=1.0, precision=None):
     N = B.shape[1] if trans_b else B.shape[2]
     dev = A.device
     with torch.cuda.device(dev):
-        C = torch.empty(nb, M, N, device=dev, dtype=torch.float32)
+        C = _empty(nb, M, N, device=dev, dtype=torch.float32)
         ws = _ws(L.egm_bmm_workspace(nb, M, N, K, prec), dev)
         _lib.check(L.egm_bmm(A.data_ptr(), int(trans_a), B.data_ptr(), int(trans_b), nb, M, N, K,
                              float(alpha), C.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream(dev)),

@@ -788,3 +788,55 @@ def test_whole_step_is_cuda_graph_capturable(pkg, dev):
         want = [out_e, a.grad, p.grad, gpf.alpha_coeffs.grad, head.second_net[0].weight.grad]
         for x, y in zip(got, want):
             assert torch.equal(x, y)                # deterministic kernels: bit-identical
+
+
+# ------------------------------------------------------------------- uninitialised-memory check
+def _every_path(pkg, dev, B, N, D):
+    """Outputs and gradients of every code path of the package on one seeded problem."""
+    EF = pkg.functional
+    res = []
+    a0, p0 = make_inputs(B, N, D, seed=5)
+    dout = torch.randn(B, 24, generator=torch.Generator().manual_seed(6)).to(dev)
+    labels = torch.arange(B) % 2
+    for mode, algo, fast in (("fp32", "dense", True), ("fp32", "dense", False), ("bf16", "dense", True),
+                             ("fp32", "lowrank", True), ("fp32_simt", "dense", True)):
+        torch.manual_seed(0)
+        gpf = pkg.GraphPolynomialFusion(3, 2).to(dev)
+        head = pkg.MomentHead(D, 24, use_third_order=True, isqrt_iterations=4, sketch_dim=64).to(dev).eval()
+        EF.set_symmetric_fast_path(fast)
+        EF.set_ns_algorithm(algo)
+        try:
+            with EF.precision(mode):
+                a = a0.to(dev).requires_grad_(True)
+                p = p0.to(dev).requires_grad_(True)
+                G = gpf(a, p)
+                out = head(a, G)
+                loss = (out * dout).sum() + EF.graph_alignment_loss(G, labels.to(dev))
+                loss.backward()
+        finally:
+            EF.set_symmetric_fast_path(True)
+            EF.set_ns_algorithm("dense")
+        res += [out.detach(), a.grad, p.grad, gpf.alpha_coeffs.grad, head.second_net[0].weight.grad,
+                head.third_net[0].weight.grad]
+    with torch.no_grad():
+        M = torch.randn(B, D, D, generator=torch.Generator().manual_seed(7)).to(dev)
+        M = M @ M.transpose(1, 2)
+        res += [pkg.NewtonSchulzSqrtm(3)(M), EF.half_vectorize(M), EF.similarity_matrix(a0.to(dev))]
+    return res
+
+
+@pytest.mark.parametrize("shape", [(2, 50, 136), (1, 40, 520)])
+def test_no_kernel_reads_memory_nobody_wrote(pkg, dev, shape):
+    """EGM_POISON: every buffer the package allocates (outputs, saved state, scratch, the absent blocks
+    of the symmetric storage) starts as 0xFF bytes = NaN. All kernels are deterministic, so the results
+    must be bit-identical to the unpoisoned run - and finite."""
+    EF = pkg.functional
+    clean = _every_path(pkg, dev, *shape)
+    EF.set_poison(True)
+    try:
+        poisoned = _every_path(pkg, dev, *shape)
+    finally:
+        EF.set_poison(False)
+    for x, y in zip(clean, poisoned):
+        assert torch.isfinite(y).all()
+        assert torch.equal(x, y)
