@@ -274,6 +274,12 @@ __device__ __forceinline__ void poly_pair_coords(int pair, int nt, int& ti, int&
   while (pair >= nt - ti) { pair -= nt - ti; ++ti; }
   tj = ti + pair;
 }
+// A pair whose column tile is the ragged last one (n % 32 columns) is walked from its mirror instead:
+// the direct tile then has n % 32 full-width rows (whole warps skip the rest) rather than 32 rows with
+// n % 32 active lanes each. The element-pair arithmetic is symmetric in the two roles.
+__device__ __forceinline__ void poly_prefer_full_rows(int n, int& ti, int& tj) {
+  if (tj != ti && tj == poly_tiles(n) - 1 && (n % kPT) != 0) { const int t = ti; ti = tj; tj = t; }
+}
 
 template <int MD>
 __global__ void __launch_bounds__(256)
@@ -512,6 +518,7 @@ gpf_poly3_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
   poly.load(coef, P, Q);
   int ti, tj;
   poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  poly_prefer_full_rows(n, ti, tj);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float* ra_b = Ra + (long long)blockIdx.y * n * ldR;
   const float* rp_b = Rp + (long long)blockIdx.y * n * ldR;
@@ -533,6 +540,8 @@ gpf_poly3_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = ty + 8 * k;
+    g2[k] = 0.f;
+    if (i0 + r >= n) continue;   // warp-uniform: a warp owns one row of the tile
     const float f = poly.eval(xa[k], xp[k]);
     const float ft = poly.eval(sa[tx][r], sp[tx][r]);
     const float g1 = fmaxf(symmetric ? 0.5f * (f + ft) : f, 0.f);
@@ -561,6 +570,7 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
   poly.load(coef, P, Q);
   int ti, tj;
   poly_pair_coords(blockIdx.x, poly_tiles(n), ti, tj);
+  poly_prefer_full_rows(n, ti, tj);
   const bool offdiag = ti != tj;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float* ra_b = Ra + (long long)blockIdx.y * n * ldR;
@@ -588,6 +598,8 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = ty + 8 * k;
+    ea_k[k] = ep_k[k] = 0.f;
+    if (i0 + r >= n) continue;   // warp-uniform: a warp owns one row of the tile
     float f, fa, fb, ft, fat, fbt, pa[4], pb[4], pat[4], pbt[4];
     poly.eval_grad(xa[k], xp[k], f, fa, fb, pa, pb);
     poly.eval_grad(sa[tx][r], sp[tx][r], ft, fat, fbt, pat, pbt);
