@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                   const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
                   const uint64_t bl = ptx::smem_desc_sw128(sB + kTileB + kk * b_step, b_lbo, 1024);
                   ptx::mma_bf16_ss(d_tmem, al, bh, idesc, (kk == 0) ? accumulate : 1u);
-                  ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
                   ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
+                  ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
                 } else {
                   ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, (kk == 0) ? accumulate : 1u);
                 }
@@ -818,9 +818,11 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
                 if (NPASS == 3) {
                   const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
                   const uint64_t bl = ptx::smem_desc_sw128(sB + kTileBh + kk * b_step, b_lbo, 1024);
+                  // neighbouring MMAs share an operand (bh, then ah); A/B on one box: -1.5 % on the
+                  // one-term products against the (al bh, ah bl, ah bh) order, nothing on two-term ones
                   ptx::mma_bf16_ss_2sm(d_tmem, al, bh, idesc, (kk == 0) ? accumulate : 1u);
-                  ptx::mma_bf16_ss_2sm(d_tmem, ah, bl, idesc, 1u);
                   ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, 1u);
+                  ptx::mma_bf16_ss_2sm(d_tmem, ah, bl, idesc, 1u);
                 } else {
                   ptx::mma_bf16_ss_2sm(d_tmem, ah, bh, idesc, (kk == 0) ? accumulate : 1u);
                 }
