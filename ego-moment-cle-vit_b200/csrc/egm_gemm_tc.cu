@@ -200,30 +200,28 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   return r;
 }
 
-// one lane's row of a 32 x 32 chunk -> packed bf16 hi words and the fp32 residuals' packed lo words
-__device__ __forceinline__ void split_row(const float (&o)[32], uint32_t (&hw)[16], uint32_t (&lw)[16],
-                                          bool has_lo) {
-#pragma unroll
-  for (int w = 0; w < 16; ++w) {
-    hw[w] = cvt_bf16x2(o[2 * w + 1], o[2 * w]);
-    if (has_lo)
-      lw[w] = cvt_bf16x2(o[2 * w + 1] - __uint_as_float(hw[w] & 0xFFFF0000u),
-                         o[2 * w] - __uint_as_float(hw[w] << 16));
-  }
-}
-// 16 packed words of one lane's row -> a 2 KiB plane staging area (rows of 64 B, 64B swizzle)
-__device__ __forceinline__ void stage_words(uint32_t buf, int lane, const uint32_t (&w)[16]) {
+// one lane's row of a 32 x 32 chunk -> a 2 KiB plane staging area (rows of 64 B, 64B swizzle): the
+// bf16 hi plane (LO = false) or the bf16 plane of the residuals x - hi (LO = true). Four words at a
+// time, so no 16-word arrays stay live next to the chunk and the TMEM load in flight.
+template <bool LO>
+__device__ __forceinline__ void stage_plane(uint32_t buf, int lane, const float (&o)[32]) {
   const uint32_t sw = (lane >> 1) & 3;       // 64B swizzle: 16B chunk ^= addr bits [7,9)
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    ptx::sts128(buf + lane * 64 + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  for (int j = 0; j < 4; ++j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x1 = o[j * 8 + 2 * q + 1], x0 = o[j * 8 + 2 * q];
+      const uint32_t h = cvt_bf16x2(x1, x0);
+      w[q] = LO ? cvt_bf16x2(x1 - __uint_as_float(h & 0xFFFF0000u), x0 - __uint_as_float(h << 16)) : h;
+    }
+    ptx::sts128(buf + lane * 64 + ((j ^ sw) << 4), w[0], w[1], w[2], w[3]);
+  }
 }
 // one lane's row of a 32 x 32 chunk -> bf16 hi/lo staging slot (hi at +0, lo at +2048)
 __device__ __forceinline__ void stage_planes(uint32_t buf, int lane, const float (&o)[32], bool has_lo) {
-  uint32_t hw[16], lw[16];
-  split_row(o, hw, lw, has_lo);
-  stage_words(buf, lane, hw);
-  if (has_lo) stage_words(buf + 2048, lane, lw);
+  stage_plane<false>(buf, lane, o);
+  if (has_lo) stage_plane<true>(buf + 2048, lane, o);
 }
 
 // Plane output of one chunk: TMA store through the warp's staging slot when the layout allows
@@ -237,14 +235,11 @@ __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, con
                                              int row, int row0, int col0, int ncols, bool row_ok,
                                              int lane, uint32_t buf, int& half_slot, bool split) {
   if (tma) {
-    uint32_t hw[16], lw[16];
-    split_row(o, hw, lw, lo != nullptr);
     if (lo && !split) {
       // one bulk group per chunk: the whole slot must have drained
       if (lane == 0) ptx::bulk_wait_read<0>();
       __syncwarp();
-      stage_words(buf, lane, hw);
-      stage_words(buf + 2048, lane, lw);
+      stage_planes(buf, lane, o, true);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -258,7 +253,7 @@ __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, con
     if (!lo) half_slot ^= 1;
     if (lane == 0) ptx::bulk_wait_read<1>();   // the store that last used this half has drained
     __syncwarp();
-    stage_words(hbuf, lane, hw);
+    stage_plane<false>(hbuf, lane, o);
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -268,7 +263,7 @@ __device__ __forceinline__ void store_planes(const float (&o)[32], bool tma, con
     if (lo) {
       if (lane == 0) ptx::bulk_wait_read<1>();
       __syncwarp();
-      stage_words(buf + 2048, lane, lw);
+      stage_plane<true>(buf + 2048, lane, o);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -312,11 +307,35 @@ __device__ __forceinline__ float epilogue_tile(const TcParams& p, uint32_t t_add
   if (p.X_hi)
     while (c_begin < c_end && n0 + c_begin * 32 + 31 < row0) ++c_begin;
   if (c_begin >= c_end) return 0.f;
+  // The addend E / dot operand F of a chunk is a dependent global load in the middle of the chunk's
+  // work (a DRAM miss: the matrix was written by an earlier launch and is larger than L2). A cache
+  // prefetch of the NEXT chunk's lines, issued before this chunk is converted and stored, hides that
+  // latency at no register cost (holding the data itself would take 32 registers of a 168 budget).
+  auto prefetch_ef = [&](int col0) {
+    if (!row_ok || col0 >= p.N) return;
+    if (p.e_mode) {
+      const int es = p.e_mode == 1 ? 2 : 4;
+      const char* e0 = static_cast<const char*>(p.E0) + ((long long)b * p.bsE + (long long)row * p.ldE + col0) * es;
+      ptx::prefetch_l2(e0);
+      if (p.e_mode == 1 && p.E1)
+        ptx::prefetch_l2(static_cast<const char*>(p.E1) + ((long long)b * p.bsE + (long long)row * p.ldE + col0) * es);
+    }
+    if (p.f_mode) {
+      const int fs = p.f_mode == 1 ? 2 : 4;
+      const char* f0 = static_cast<const char*>(p.F0) + ((long long)b * p.bsF + (long long)row * p.ldF + col0) * fs;
+      ptx::prefetch_l2(f0);
+      if (p.f_mode == 1 && p.F1)
+        ptx::prefetch_l2(static_cast<const char*>(p.F1) + ((long long)b * p.bsF + (long long)row * p.ldF + col0) * fs);
+    }
+  };
+  const bool has_ef = p.e_mode || p.f_mode;
+  if (has_ef) prefetch_ef(n0 + c_begin * 32);
   uint32_t v[32];
   ptx::tmem_ld_32x32(t_addr + c_begin * 32, v);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const int col0 = n0 + c * 32;
+    if (has_ef && c + 1 < c_end) prefetch_ef(col0 + 32);
     ptx::tmem_ld_wait();
     float o[32];
 #pragma unroll

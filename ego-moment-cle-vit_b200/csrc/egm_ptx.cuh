@@ -84,6 +84,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tensormap(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* gptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr));
+}
 __device__ __forceinline__ void tma_load_3d(const void* desc, uint32_t bar, uint32_t dst,
                                             int c0, int c1, int c2) {
   asm volatile(
