@@ -283,3 +283,22 @@ def test_shard_bounds_cover_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         d.shard_bounds(4, 2, 2)
+
+
+# ------------------------------------------------------------------------- bench.py contract
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line
+    with the metric / config of the native arm, `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "MomentHead+GPF fwd+bwd images/sec"
+    assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[1]") and d["config"]["tokens"] == 197
