@@ -5,7 +5,7 @@
 // :292-293 pooling products, src/models/gpf_kernel.py:88 Gram) and the elementwise passes
 // around them (`3*I - ZY`, `0.5 *`, `/ sqrt(trace)`), which are folded into the epilogue.
 //
-// Shape of the kernel (one persistent CTA per SM, 320 threads; default: CTA pairs, see below):
+// Shape of the kernel (one persistent CTA per SM, 320 threads; CTAs work in pairs, see below):
 //   warp 0      TMA producer: cp.async.bulk.tensor 3-D boxes {64 x rows x 1 image} of the
 //               bf16 operand planes into 128B-swizzled shared memory, mbarrier-signalled
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::f16 (128 x 256 x 16, or 256 x 256 x 16
@@ -48,7 +48,6 @@ constexpr int BN = 256;        // tile cols  (= UMMA N, one TMEM column per col)
 constexpr int BK = 64;         // K per pipeline stage: 64 bf16 = one 128-byte swizzle line
 constexpr int UK = 16;         // K per tcgen05.mma (bf16)
 constexpr int kTileA = BM * BK * 2;   // 16 KiB per plane
-constexpr int kTileB = BN * BK * 2;   // 32 KiB per plane
 constexpr int kChunk = BK * 128;      // one MN-major TMA box: 64 K-rows x 128 B = 8 KiB
 constexpr int kEpiWarps = 8;          // two per TMEM lane quarter, each takes half of the columns
 constexpr int kThreads = 32 * (2 + kEpiWarps);
@@ -99,14 +98,6 @@ struct alignas(64) TcParams {
   __nv_bfloat16* X_hi;
   __nv_bfloat16* X_lo;
   long long ldX;
-};
-
-template <int NPASS>
-struct Cfg {
-  static constexpr int kPlanes = (NPASS == 3) ? 2 : 1;
-  static constexpr int kStageBytes = kPlanes * (kTileA + kTileB);      // 96 KiB / 48 KiB
-  static constexpr int kStages = (NPASS == 3) ? 2 : 4;                 // 192 KiB of operands
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -451,226 +442,13 @@ __global__ void dot_reduce_kernel(const float* __restrict__ ws, int per_img, int
   if (lane == 0) out[b] = a;
 }
 
-template <int NPASS>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-  using C = Cfg<NPASS>;
-  extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle atoms are 1024 B: align the operand ring.
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;
-  const uint32_t bar_base = epi_base + kEpiBytes;
-  // barrier block: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
-  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::kStages * C::kStageBytes + kEpiBytes +
-                                           8 * (2 * C::kStages + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int t = 0; t < p.nterms; ++t)
-      for (int i = 0; i < 4; ++i)
-        if (i % 2 == 0 || NPASS == 3) ptx::prefetch_tensormap(&p.tm[t][i]);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < C::kStages; ++s) {
-        ptx::mbar_init(full_bar(s), 1);
-        ptx::mbar_init(empty_bar(s), 1);
-      }
-      for (int a = 0; a < 2; ++a) {
-        ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), kEpiWarps);  // one arrive per epilogue warp
-      }
-      ptx::fence_barrier_init();
-    }
-    __syncwarp();
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  const int tiles_per_img = p.tiles_per_img;
-  const int ntiles = tiles_per_img * p.batch;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    // The whole warp runs the loop (warp-uniform control flow keeps addresses, coordinates and
-    // descriptors in uniform registers); one elected lane issues the copies.
-    {
-      const bool issuer = ptx::elect_one();
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_img;
-        const int r = tile - b * tiles_per_img;
-        int tm, tn;
-        tile_coords(p, r, tm, tn);
-        const int m0 = tm * BM;
-        const int n0 = tn * BN;
-        const int bl = p.splits > 1 ? 0 : b;   // batch coordinate of the operand loads
-        for (int t = 0; t < p.nterms; ++t) {
-          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
-          const int a_kboxes = a_sym ? BM / 64 : 1;   // symmetric operands use 64-row boxes in
-          const int b_kboxes = b_sym ? BN / 64 : 1;   // both major-nesses (one tensor map)
-          const int nkb_all = (p.K[t] + BK - 1) / BK;
-          const int kb_lo = p.splits > 1 ? (int)((long long)b * nkb_all / p.splits) : 0;
-          const int kb_hi = p.splits > 1 ? (int)((long long)(b + 1) * nkb_all / p.splits) : nkb_all;
-          for (int kb = kb_lo; kb < kb_hi; ++kb) {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t fb = full_bar(stage);
-            const uint32_t sA = smem_base + stage * C::kStageBytes;
-            const uint32_t sB = sA + C::kPlanes * kTileA;
-            const int k0 = kb * BK;
-            const int a_mn = a_sym ? sym_a_mn(m0, k0) : p.a_mn[t];
-            const int b_mn = b_sym ? sym_b_mn(k0, n0) : p.b_mn[t];
-            if (issuer) {
-              ptx::mbar_arrive_expect_tx(fb, C::kStageBytes);
-#pragma unroll
-              for (int pl = 0; pl < C::kPlanes; ++pl) {
-                if (!a_mn) {
-                  for (int j = 0; j < a_kboxes; ++j)
-                    ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, k0, m0 + 64 * j, bl);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < BM / 64; ++j)
-                    ptx::tma_load_3d(&p.tm[t][pl], fb, sA + pl * kTileA + j * kChunk, m0 + 64 * j, k0, bl);
-                }
-                if (!b_mn) {
-                  for (int j = 0; j < b_kboxes; ++j)
-                    ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk, k0, n0 + 64 * j, bl);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < BN / 64; ++j)
-                    ptx::tma_load_3d(&p.tm[t][2 + pl], fb, sB + pl * kTileB + j * kChunk,
-                                     n0 + 64 * j, k0, bl);
-                }
-              }
-            }
-            __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    // warp-uniform loop, one elected lane issues (and therefore also commits) every MMA
-    {
-      const bool issuer = ptx::elect_one();
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int bt = tile / tiles_per_img;
-        int tm, tn;
-        tile_coords(p, tile - bt * tiles_per_img, tm, tn);
-        const int m0 = tm * BM, n0 = tn * BN;
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        for (int t = 0; t < p.nterms; ++t) {
-          const int a_sym = p.a_sym[t], b_sym = p.b_sym[t];
-          const int nkb_all = (p.K[t] + BK - 1) / BK;
-          const int kb_lo = p.splits > 1 ? (int)((long long)bt * nkb_all / p.splits) : 0;
-          const int kb_hi = p.splits > 1 ? (int)((long long)(bt + 1) * nkb_all / p.splits) : nkb_all;
-          for (int kb = kb_lo; kb < kb_hi; ++kb) {
-            const int a_mn = a_sym ? sym_a_mn(m0, kb * BK) : p.a_mn[t];
-            const int b_mn = b_sym ? sym_b_mn(kb * BK, n0) : p.b_mn[t];
-            const uint32_t idesc = ptx::idesc_bf16_f32(BM, BN, a_mn, b_mn);
-            const uint32_t a_step = a_mn ? 2048u : 32u;   // bytes per 16-wide K step
-            const uint32_t b_step = b_mn ? 2048u : 32u;
-            const uint32_t a_lbo = a_mn ? kChunk : 0u;
-            const uint32_t b_lbo = b_mn ? kChunk : 0u;
-            ptx::mbar_wait(full_bar(stage), phase);
-            ptx::tc_fence_after();
-            const uint32_t sA = smem_base + stage * C::kStageBytes;
-            const uint32_t sB = sA + C::kPlanes * kTileA;
-            if (issuer) {
-#pragma unroll
-              for (int kk = 0; kk < BK / UK; ++kk) {
-                const uint64_t ah = ptx::smem_desc_sw128(sA + kk * a_step, a_lbo, 1024);
-                const uint64_t bh = ptx::smem_desc_sw128(sB + kk * b_step, b_lbo, 1024);
-                if (NPASS == 3) {
-                  const uint64_t al = ptx::smem_desc_sw128(sA + kTileA + kk * a_step, a_lbo, 1024);
-                  const uint64_t bl = ptx::smem_desc_sw128(sB + kTileB + kk * b_step, b_lbo, 1024);
-                  ptx::mma_bf16_ss(d_tmem, al, bh, idesc, (kk == 0) ? accumulate : 1u);
-                  ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, 1u);
-                  ptx::mma_bf16_ss(d_tmem, ah, bl, idesc, 1u);
-                } else {
-                  ptx::mma_bf16_ss(d_tmem, ah, bh, idesc, (kk == 0) ? accumulate : 1u);
-                }
-              }
-              ptx::tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
-            }
-            __syncwarp();
-            accumulate = 1u;
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-        if (issuer) ptx::tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which half of the tile's columns
-    const int cb = half * (BN / 64), ce = cb + BN / 64;
-    int half_slot = 0;                  // persists across tiles: a store may still be in flight
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_img;
-      const int r = tile - b * tiles_per_img;
-      int tm, tn;
-      tile_coords(p, r, tm, tn);
-      const int m0 = tm * BM;
-      const int n0 = tn * BN;
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
-      ptx::tc_fence_after();
-      const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
-                                     m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
-      if (p.dot_ws)
-        write_dot_partial(p, (p.sym_out && (n0 >> 8) > (m0 >> 8)) ? 2.f * ds : ds, lane,
-                          (long long)tile * kEpiWarps + (warp - 2));
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-    if (lane == 0) ptx::bulk_wait_all();   // staging slots must outlive their TMA stores
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-
-// ------------------------------------------------------------------ 2-CTA variant
+// ------------------------------------------------------------------ the kernel
 // A CTA pair (cluster of 2, one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 rows of A and HALF of B's 256 columns, so the shared-memory
-// fill per MMA cycle drops by a third versus the 1-CTA kernel and the freed space buys a
+// fill per MMA cycle is a third below a single CTA's 128 x 256 tile and the freed space buys a
 // deeper ring (3 x 64 KiB stages for bf16x3, 6 x 32 KiB for single pass). Only the leader CTA
-// issues MMAs; its commits are multicast to the mbarriers of both CTAs.
+// issues MMAs; its commits are multicast to the mbarriers of both CTAs. (A single-CTA variant of
+// this kernel measured 1155 TFLOP/s executed against 1334 for the pair in round 1 and was retired.)
 constexpr int kTileBh = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the B tile
 
 template <int NPASS>
@@ -977,29 +755,6 @@ bool plane_ok(const Mat& m, int batch, bool need_lo) {
 }
 
 template <int NPASS>
-cudaError_t launch(const TcParams& p, cudaStream_t stream) {
-  using C = Cfg<NPASS>;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (configured_dev != dev) {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured_dev = dev;
-  }
-  int sms = 0;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return e;
-  const long long ntiles = (long long)p.tiles_per_img * p.batch;
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  gemm_tc_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
-  note_launch();
-  return cudaGetLastError();
-}
-
-template <int NPASS>
 cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   using C = Cfg2<NPASS>;
   static thread_local int configured_dev = -1;
@@ -1035,14 +790,7 @@ int epi_split_for(int total_k) {
   return forced >= 0 ? forced : (total_k >= 512 ? 1 : 0);
 }
 
-// EGM_GEMM_CTAS=1 selects the single-CTA kernel (kept for A/B measurements); default is the pair.
-int tc_ctas() {
-  static int v = []() {
-    const char* e = getenv("EGM_GEMM_CTAS");
-    return (e && e[0] == '1') ? 1 : 2;
-  }();
-  return v;
-}
+constexpr int kCtas = 2;   // CTAs per tile (cta_group::2)
 
 }  // namespace
 
@@ -1068,7 +816,7 @@ static int count_tiles(int tiles_m, int tiles_n, int tile_rows, bool triu) {
 
 size_t gemm_tc_dot_ws_floats(const GemmProblem& g) {
   if (!g.dot_out) return 0;
-  const int ctas = tc_ctas();
+  const int ctas = kCtas;
   const int tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   const int tiles_n = (g.N + BN - 1) / BN;
   return (size_t)g.batch * tiles_m * tiles_n * kEpiWarps * ctas;
@@ -1090,7 +838,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
   p.batch = g.batch;
   p.nterms = g.nterms;
   p.splits = 1;
-  const int ctas = tc_ctas();
+  const int ctas = kCtas;
   p.tiles_m = (g.M + ctas * BM - 1) / (ctas * BM);
   p.tiles_n = (g.N + BN - 1) / BN;
   p.tile_rows = ctas * BM;
@@ -1231,8 +979,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     prof_id = prof_begin(stream, flops, dims);
   }
   cudaError_t le;
-  if (ctas == 2) le = npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
-  else le = npass == 3 ? launch<3>(p, stream) : launch<1>(p, stream);
+  le = npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);
   if (prof_id >= 0) prof_end(prof_id, stream);
   if (le != cudaSuccess) return le;
   if (g.dot_out) {
