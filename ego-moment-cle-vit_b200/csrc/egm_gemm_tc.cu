@@ -61,6 +61,7 @@ struct alignas(64) TcParams {
   CUtensorMap tmC2[2];   // TMA-store maps of the secondary plane output
   int tma_cp, tma_cf, tma_c2;  // which outputs leave through TMA stores
   int epi_split;         // hi and lo plane stores of a chunk as separate bulk groups
+  unsigned epi_sleep_ns; // back-off of the epilogue warps while they wait for an accumulator
   int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
@@ -652,7 +653,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       tile_coords(p, r, tm, tn);
       const int m0 = tm * (2 * BM) + rank * BM;
       const int n0 = tn * BN;
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::mbar_wait_relaxed(tfull_bar(acc), acc_phase, p.epi_sleep_ns);
       ptx::tc_fence_after();
       const float ds = epilogue_tile(p, tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16), b,
                                      m0 + q * 32, lane, n0, epi_base + (warp - 2) * kEpiWarpBytes, cb, ce, half_slot);
@@ -886,6 +887,11 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     }
   }
   p.epi_split = epi_split_for(g.t[0].K + (g.nterms > 1 ? g.t[1].K : 0));
+  {
+    // 256 ns: -0.5 % Newton-Schulz time against pure spinning (A/B on one box); EGM_EPI_SLEEP_NS overrides
+    static unsigned ns = []() { const char* e = getenv("EGM_EPI_SLEEP_NS"); return e ? (unsigned)atoi(e) : 256u; }();
+    p.epi_sleep_ns = ns;
+  }
   if (g.split_k > 1) {
     // K-slices of one product; slice s writes partial sums to output batch index s
     const int nkb = (g.t[0].K + BK - 1) / BK;
