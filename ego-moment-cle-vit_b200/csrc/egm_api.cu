@@ -40,8 +40,8 @@ struct NsState {
 // triangle in bf16 planes (X: the operand of second_net's Linear; lower tiles are not computed).
 // `sym`: A is symmetric, so every matrix of the chain is; all of them are kept in the engine's
 // symmetric block storage (GemmTerm::symA) and only the upper tiles of each product are evaluated.
-int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, const W* X, cudaStream_t st,
-                    bool sym = false) {
+int ns_products_fwd_impl(const NsState& S, int prec, const float* post, float* O, const W* X,
+                         cudaStream_t st, bool sym) {
   const int B = S.B, D = S.D, K = S.K;
   const long long dd = (long long)D * D;
   auto prod = [&](const W& a, const W& b) {
@@ -109,7 +109,7 @@ struct NsFinal {
 };
 
 // Backward products (K >= 2). buf[0] holds dY_K = post * dO on entry; buf[1..5] are scratch.
-int ns_products_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+int ns_products_bwd_impl(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
   const int B = S.B, D = S.D, K = S.K;
   const long long dd = (long long)D * D;
   W dY = buf[0], dYn = buf[1], dZ = buf[2], dZn = buf[3], dP = buf[4], X = buf[5];
@@ -187,7 +187,7 @@ int ns_products_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cuda
 //   T'_k = -(Z'_k Y_k + Z_k Y'_k)/2,  Y'_{k+1} = Y'_k T_k + Y_k T'_k,  Z'_{k+1} = T'_k Z_k + T_k Z'_k
 // buf[0] holds Y'_1 = -post*sym(dO)/2 on entry (symmetric block storage); buf[1..4] are scratch.
 // The result dA = Y'_K goes to fin.dA_w with <dA, A> in fin.dot_out.
-int ns_tangent_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+int ns_tangent_bwd_impl(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
   const int B = S.B, D = S.D, K = S.K;
   W Yd = buf[0], Zd = buf[1], Td = buf[2], Ydn = buf[3], Zdn = buf[4];
   auto two = [&](GemmProblem& g, const W& a0, const W& b0, const W& a1, const W& b1) {
@@ -241,6 +241,27 @@ int ns_tangent_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaS
   return EGM_OK;
 }
 
+
+// The chains as the benchmark's roofline sees them: under egm_prof_enable(2) all launches of one chain
+// share one pair of CUDA events (the launches in between keep their dependent-launch overlap).
+struct ProfGroupScope {
+  cudaStream_t st;
+  explicit ProfGroupScope(cudaStream_t s) : st(s) { prof_group_begin(st); }
+  ~ProfGroupScope() { prof_group_end(st); }
+};
+int ns_products_fwd(const NsState& S, int prec, const float* post, float* O, const W* X, cudaStream_t st,
+                    bool sym = false) {
+  ProfGroupScope scope(st);
+  return ns_products_fwd_impl(S, prec, post, O, X, st, sym);
+}
+int ns_products_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+  ProfGroupScope scope(st);
+  return ns_products_bwd_impl(S, prec, buf, fin, st);
+}
+int ns_tangent_bwd(const NsState& S, int prec, W* buf, const NsFinal& fin, cudaStream_t st) {
+  ProfGroupScope scope(st);
+  return ns_tangent_bwd_impl(S, prec, buf, fin, st);
+}
 
 // Tail of the pooling backward given V1 = Zc dM^T and V2 = Zc dM:
 //   dZc = Wn V1 + Wn^T V2, dW = V2 Zc^T, then centring / weighted mean / degree normalisation.

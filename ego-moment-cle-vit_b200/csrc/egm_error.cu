@@ -35,10 +35,44 @@ std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 std::atomic<int> g_prof_on{0};
 }
-bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
-void prof_enable(int on) {
+// level 1: every launch is bracketed; level 2: only the groups the chains open (a Newton-Schulz chain =
+// one record), so the launches inside keep their programmatic-dependent-launch overlap
+int prof_level() { return g_prof_on.load(std::memory_order_relaxed); }
+bool prof_enabled() { return prof_level() != 0; }
+void prof_enable(int level) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  g_prof_on.store(on ? 1 : 0);
+  g_prof_on.store(level < 0 ? 0 : (level > 2 ? 2 : level));
+}
+namespace {
+struct ProfGroup { int id = -1; double flops = 0; int launches = 0; int dims[6] = {0, 0, 0, 0, 0, 0}; };
+thread_local ProfGroup t_group;
+}
+bool prof_group_open() { return t_group.id >= 0; }
+void prof_group_begin(cudaStream_t st) {
+  if (prof_level() != 2 || t_group.id >= 0) return;
+  const int zero[6] = {0, 0, 0, 0, 0, 0};
+  t_group = ProfGroup();
+  t_group.id = prof_begin(st, 0.0, zero);
+}
+void prof_group_note(double flops, const int dims[6]) {
+  if (t_group.id < 0) return;
+  t_group.flops += flops;
+  if (t_group.launches++ == 0)
+    for (int i = 0; i < 6; ++i) t_group.dims[i] = dims[i];
+}
+void prof_group_end(cudaStream_t st) {
+  if (t_group.id < 0) return;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (t_group.id < (int)g_prof.size()) {
+      ProfRec& r = g_prof[t_group.id];
+      r.flops = t_group.flops;
+      for (int i = 0; i < 6; ++i) r.dims[i] = t_group.dims[i];
+      r.dims[3] = -t_group.launches;   // a negative "K of term 1" marks a group of that many launches
+      cudaEventRecord(r.e1, st);
+    }
+  }
+  t_group = ProfGroup();
 }
 void prof_reset() {
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -102,7 +102,13 @@ void set_error(const char* fmt, ...);
 
 // optional per-launch timing of the tcgen05 engine (egm_error.cu; C ABI egm_prof_*)
 bool prof_enabled();
-void prof_enable(int on);
+int prof_level();                   // 0 off, 1 every launch, 2 chain groups only
+void prof_enable(int level);
+// level 2: one record for all engine launches between begin and end (same thread, same stream)
+bool prof_group_open();
+void prof_group_begin(cudaStream_t st);
+void prof_group_note(double flops, const int dims[6]);
+void prof_group_end(cudaStream_t st);
 void prof_reset();
 int prof_begin(cudaStream_t st, double flops, const int dims[6]);   // dims: M, N, K0, K1, batch, passes
 void prof_end(int id, cudaStream_t st);

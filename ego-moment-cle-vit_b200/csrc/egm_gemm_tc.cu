@@ -507,6 +507,10 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // programmatic dependent launch: the set-up above may overlap the tail of the previous kernel of the
+  // stream; nothing below touches global memory before that kernel has completed
+  ptx::griddep_launch_dependents();
+  ptx::griddep_wait();
 
   const int tiles_per_img = p.tiles_per_img;             // tiles_m counts 256-row tiles here
   const int ntiles = tiles_per_img * p.batch;
@@ -755,6 +759,12 @@ bool plane_ok(const Mat& m, int batch, bool need_lo) {
   return true;
 }
 
+// EGM_PDL=0 turns programmatic dependent launch off (A/B switch)
+bool pdl_enabled() {
+  static bool on = []() { const char* e = getenv("EGM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int NPASS>
 cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   using C = Cfg2<NPASS>;
@@ -774,9 +784,19 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   const long long ntiles = (long long)p.tiles_per_img * p.batch;
   const long long pairs = sms / 2;
   const int grid = 2 * (int)(ntiles < pairs ? ntiles : pairs);
-  gemm_tc2_kernel<NPASS><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<NPASS>, p);
   note_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // hi and lo plane stores of a chunk as one bulk group or two. Two groups keep a store in flight while
@@ -982,7 +1002,8 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
     for (int t = 0; t < g.nterms; ++t) flops += 2.0 * g.M * g.N * (double)g.t[t].K * g.batch;
     if (p.triu_tiles) flops *= (double)p.tiles_per_img / (p.tiles_m * p.tiles_n);
     const int dims[6] = {g.M, g.N, g.t[0].K, g.nterms > 1 ? g.t[1].K : 0, g.batch, npass};
-    prof_id = prof_begin(stream, flops, dims);
+    if (prof_level() == 1) prof_id = prof_begin(stream, flops, dims);
+    else prof_group_note(flops, dims);
   }
   cudaError_t le;
   le = npass == 3 ? launch2<3>(p, stream) : launch2<1>(p, stream);

@@ -95,6 +95,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
   }
 }
 
+// ------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute may start while the
+// previous kernel of the stream is still draining: everything before griddep_wait() (barrier init,
+// TMEM allocation, tensor-map prefetch, cluster sync) overlaps that tail; griddep_wait() returns
+// once the previous grid has completed and its memory is visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");

@@ -59,11 +59,13 @@ int egm_version(void);
 const char* egm_last_error(void);
 /* kernels launched by this library in this process so far (monotonic; bench.py's gpu_launches) */
 unsigned long long egm_launch_count(void);
-/* Optional per-launch timing of the tcgen05 GEMM engine (bench.py's roofline): while enabled,
- * every engine launch is bracketed by two CUDA events on its own stream. egm_prof_read(i)
- * synchronises on launch i and returns its duration, its algorithmic flops and
- * dims = {M, N, K of term 0, K of term 1 (0 if absent), batch, MMA passes per product}. */
-void egm_prof_enable(int on);
+/* Optional timing of the tcgen05 GEMM engine (bench.py's roofline). level 1: every engine launch is
+ * bracketed by two CUDA events on its own stream; level 2: one pair of events around each
+ * Newton-Schulz chain instead (the launches inside keep their dependent-launch overlap); 0: off.
+ * egm_prof_read(i) synchronises on record i and returns its duration, its algorithmic flops and
+ * dims = {M, N, K of term 0, K of term 1 (0 if absent), batch, MMA passes per product}; for a chain
+ * record dims[3] = -(number of launches) and the other dims are those of its first launch. */
+void egm_prof_enable(int level);
 void egm_prof_reset(void);
 int egm_prof_count(void);
 int egm_prof_read(int i, float* ms, double* flops, int* dims);
