@@ -104,3 +104,43 @@ def test_graph_alignment_loss_matches_reference(tag, tol):
     assert abs(loss - float(rec[f"{tag}_loss"])) < tol * max(1.0, abs(loss))
     dG = O.graph_alignment_loss_backward(G, labels, dloss=3.0)
     assert rel_err(dG, rec[f"{tag}_dG_x3"]) < max(tol, 1e-9) * 10
+
+
+@pytest.mark.parametrize("K", [2, 3, 5])
+def test_symmetric_tangent_chain_is_the_symmetric_part_of_the_reverse_mode_gradient(K):
+    """The identity the symmetric-graph fast path rests on (csrc/egm_api.cu, ns_tangent_bwd): for a
+    symmetric M, Y_K is a fixed polynomial in A = M/(tr M + eps), its Frechet derivative is self-adjoint
+    and commutes with transposition, so the symmetric part of the reference's reverse-mode dM equals the
+    FORWARD tangent of the commuting chain along sym(dO) - every tangent being symmetric itself."""
+    rng = np.random.default_rng(K)
+    B, N, D, eps = 2, 10, 24, 1e-5
+    Z = rng.standard_normal((B, N, D))
+    M = np.einsum("bnd,bne->bde", Z, Z)                      # symmetric, rank N < D like Zc^T W Zc
+    dO = O.half_vectorize_backward(rng.standard_normal((B, D * (D + 1) // 2)), D)   # upper-triangular
+    dM_ref = O.newton_schulz_backward(M, dO, K, eps)         # the reference's gradient (not symmetric)
+    tau = np.trace(M, axis1=1, axis2=2)
+    inv, post = 1.0 / (tau + eps), (tau + eps) ** -0.5
+    A = M * inv[:, None, None]
+    I = np.eye(D)[None]
+    # the commuting forward chain of the CUDA path: Y_1 = T_0, Z_1 = T_0 A, ...
+    T = [1.5 * I - 0.5 * A]
+    Y, Zs = {1: T[0]}, {1: T[0] @ A}
+    for k in range(1, K):
+        T.append(1.5 * I - 0.5 * Zs[k] @ Y[k])
+        Y[k + 1] = Y[k] @ T[k]
+        Zs[k + 1] = T[k] @ Zs[k]
+    assert rel_err(post[:, None, None] * Y[K], O.newton_schulz(M, K, eps)) < 1e-12
+    # the tangent chain along E = post * sym(dO)
+    E = post[:, None, None] * 0.5 * (dO + np.swapaxes(dO, 1, 2))
+    Yd = -0.5 * E
+    Zd = -3.0 * Yd + Yd @ A + A @ Yd
+    for k in range(1, K):
+        Td = -0.5 * (Zd @ Y[k] + Zs[k] @ Yd)
+        Yd, Zd = Yd @ T[k] + Y[k] @ Td, Td @ Zs[k] + T[k] @ Zd
+        assert rel_err(Yd, np.swapaxes(Yd, 1, 2)) < 1e-12     # tangents stay symmetric
+    dA = Yd
+    dotO = np.einsum("bij,bij->b", dO, post[:, None, None] * Y[K])
+    dotA = np.einsum("bij,bij->b", dA, A)
+    dtau = (-0.5 * dotO - dotA) * inv
+    dM = inv[:, None, None] * dA + dtau[:, None, None] * I
+    assert rel_err(dM, 0.5 * (dM_ref + np.swapaxes(dM_ref, 1, 2))) < 1e-10
