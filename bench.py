@@ -197,6 +197,41 @@ def run_reference(args):
     }))
 
 
+def torch_eager_rates(B, dev, gpf, head, dev_inputs, d_out, timed, steps=3):
+    """images/s of the same training step written as plain torch ops (cuBLAS bmm, autograd): fp32 with
+    TF32 off (the reference's setting) and with TF32 allowed."""
+    import copy
+    import torch
+    from oracle import torch_eager as TE
+    alpha = torch.nn.Parameter(gpf.alpha_coeffs.detach().clone())
+    net = copy.deepcopy(head.second_net).to(dev).train()
+    params = [alpha] + list(net.parameters())
+    opt = torch.optim.SGD(params, lr=1e-6)
+
+    def step(i):
+        a, p = dev_inputs[i % 2]
+        a = a.detach().requires_grad_(True)
+        p = p.detach().requires_grad_(True)
+        out = TE.head_forward(a, TE.gpf_forward(a, p, alpha), net, NS_ITERS)
+        (out * d_out).sum().backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    out = {}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32 in (("torch_eager_fp32", False), ("torch_eager_tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            step(0)
+            ms = timed(step, steps) / steps
+            out[name] = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                         "note": "reference algorithm as stock torch ops + autograd on the same GPU, "
+                                 + ("allow_tf32=True" if tf32 else "fp32 (allow_tf32=False, the reference's setting)")}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
 # ------------------------------------------------------------------------------ native leg
 def run_native(args):
     import torch
@@ -400,6 +435,12 @@ def run_native(args):
                                          "note": "same function; iSQRT-COV evaluated in N x N low-rank form"}
         EF.set_ns_algorithm("dense")
         EF.set_precision(args.precision)
+        # "PyTorch on B200" comparator: the reference's algorithm as stock torch ops with
+        # autograd (oracle/torch_eager.py, pinned to the oracle) on the same GPU, same inputs and step
+        try:
+            extras.update(torch_eager_rates(B, dev, gpf, head, dev_inputs, d_out, timed))
+        except Exception as exc:          # a comparator must never take the benchmark line down
+            extras["torch_eager_error"] = repr(exc)[:200]
 
     if rank != 0:
         if world > 1:

@@ -144,3 +144,26 @@ def test_symmetric_tangent_chain_is_the_symmetric_part_of_the_reverse_mode_gradi
     dtau = (-0.5 * dotO - dotA) * inv
     dM = inv[:, None, None] * dA + dtau[:, None, None] * I
     assert rel_err(dM, 0.5 * (dM_ref + np.swapaxes(dM_ref, 1, 2))) < 1e-10
+
+
+def test_torch_eager_comparator_matches_the_oracle():
+    """oracle/torch_eager.py (bench.py's "PyTorch on B200" comparator) is the same function as the
+    numpy oracle: forward taps and autograd gradients in float64 on the CPU."""
+    import torch
+    from oracle import torch_eager as TE
+    rec = golden("small_p2q2")
+    c = _cfg(rec)
+    a = torch.from_numpy(rec["anchor"]).requires_grad_(True)
+    p = torch.from_numpy(rec["positive"]).requires_grad_(True)
+    alpha = torch.from_numpy(rec["alpha"]).requires_grad_(True)
+    G = TE.gpf_forward(a, p, alpha)
+    assert rel_err(G.detach().numpy(), rec["G"]) < 1e-12
+    vec = TE.moment_vector(a, G, c["K"])
+    assert rel_err(vec.detach().numpy(), rec["vec"]) < 1e-10
+    (vec * torch.from_numpy(rec["d_vec"])).sum().backward()
+    fw = O.gpf_forward(rec["anchor"], rec["positive"], rec["alpha"])
+    dZ, dG = O.moment_backward(rec["anchor"], fw["G"], c["K"], rec["d_vec"], 1e-5)
+    da, dp, dal = O.gpf_backward(rec["anchor"], rec["positive"], rec["alpha"], dG)
+    assert rel_err(a.grad.numpy(), da + dZ) < 1e-8
+    assert rel_err(p.grad.numpy(), dp) < 1e-8
+    assert rel_err(alpha.grad.numpy(), dal) < 1e-8
