@@ -1,10 +1,10 @@
-"""PyTorch-eager restatement of the reference algorithm - TEST / BENCHMARK INFRASTRUCTURE ONLY.
+"""PyTorch-eager restatement of the reference algorithm - BENCHMARK BASELINE ONLY (not the oracle, not the product).
 
 The "PyTorch on B200" comparator of SURVEY.md 8(d): the same arithmetic as the reference modules
 (gpf_kernel.py:75-159, moment_head.py:28-70 and :222-300) written as plain torch ops with autograd,
 so `bench.py` can time what the stock framework does with this algorithm on the same GPU (cuBLAS
 `torch.bmm`, ~120 launches for GPF, 4K matrix products forward and 8K backward for Newton-Schulz).
-The reference tree itself is not present on the GPU box. Pinned against `moment_oracle.py` (which is
+The reference tree itself is not present on the GPU box. Pinned against `oracle/moment_oracle.py` (which is
 pinned against the reference's own goldens) by tests/test_oracle_golden.py. Nothing in the product
 package imports this file.
 """

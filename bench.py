@@ -202,7 +202,7 @@ def torch_eager_rates(B, dev, gpf, head, dev_inputs, d_out, timed, steps=3):
     TF32 off (the reference's setting) and with TF32 allowed."""
     import copy
     import torch
-    from oracle import torch_eager as TE
+    from baseline import torch_eager as TE
     alpha = torch.nn.Parameter(gpf.alpha_coeffs.detach().clone())
     net = copy.deepcopy(head.second_net).to(dev).train()
     params = [alpha] + list(net.parameters())
@@ -436,7 +436,7 @@ def run_native(args):
         EF.set_ns_algorithm("dense")
         EF.set_precision(args.precision)
         # "PyTorch on B200" comparator: the reference's algorithm as stock torch ops with
-        # autograd (oracle/torch_eager.py, pinned to the oracle) on the same GPU, same inputs and step
+        # autograd (baseline/torch_eager.py, pinned to the oracle) on the same GPU, same inputs and step
         try:
             extras.update(torch_eager_rates(B, dev, gpf, head, dev_inputs, d_out, timed))
         except Exception as exc:          # a comparator must never take the benchmark line down

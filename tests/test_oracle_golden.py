@@ -147,10 +147,10 @@ def test_symmetric_tangent_chain_is_the_symmetric_part_of_the_reverse_mode_gradi
 
 
 def test_torch_eager_comparator_matches_the_oracle():
-    """oracle/torch_eager.py (bench.py's "PyTorch on B200" comparator) is the same function as the
+    """baseline/torch_eager.py (bench.py's "PyTorch on B200" comparator) is the same function as the
     numpy oracle: forward taps and autograd gradients in float64 on the CPU."""
     import torch
-    from oracle import torch_eager as TE
+    from baseline import torch_eager as TE
     rec = golden("small_p2q2")
     c = _cfg(rec)
     a = torch.from_numpy(rec["anchor"]).requires_grad_(True)
