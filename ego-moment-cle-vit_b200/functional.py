@@ -76,18 +76,18 @@ def set_poison(on: bool) -> None:
     _poison = bool(on)
 
 
-def _empty(*size, **kw) -> torch.Tensor:
-    t = torch.empty(*size, **kw)
-    if _poison:
-        t.view(torch.uint8).fill_(0xFF) if t.dtype != torch.uint8 else t.fill_(0xFF)
+def _poisoned(t: torch.Tensor) -> torch.Tensor:
+    if _poison and t.numel():
+        (t if t.dtype == torch.uint8 else t.view(torch.uint8)).fill_(0xFF)
     return t
+
+
+def _empty(*size, **kw) -> torch.Tensor:
+    return _poisoned(torch.empty(*size, **kw))
 
 
 def _empty_like(x: torch.Tensor) -> torch.Tensor:
-    t = torch.empty_like(x)
-    if _poison:
-        t.view(torch.uint8).fill_(0xFF)
-    return t
+    return _poisoned(torch.empty_like(x))
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
