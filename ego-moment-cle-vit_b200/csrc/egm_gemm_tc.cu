@@ -803,12 +803,13 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
 // the other half is restaged: -2 % on the long-K Newton-Schulz products (mainloop-bound, the epilogue
 // only has to stay out of the way), +5 % on short-K products whose time IS the epilogue (measured A/B
 // on one box). EGM_EPI_SPLIT=0/1 forces either.
-int epi_split_for(int total_k) {
+int epi_split_for(int total_k, int m) {
   static int forced = []() {
     const char* e = getenv("EGM_EPI_SPLIT");
     return !e ? -1 : (e[0] == '0' ? 0 : 1);
   }();
-  return forced >= 0 ? forced : (total_k >= 512 ? 1 : 0);
+  // long K and more than one row tile per image: the D x D x D chain products, not V = Zc dA (M = N_tokens)
+  return forced >= 0 ? forced : ((total_k >= 512 && m > 256) ? 1 : 0);
 }
 
 constexpr int kCtas = 2;   // CTAs per tile (cta_group::2)
@@ -906,7 +907,7 @@ cudaError_t gemm_tc(const GemmProblem& g, int npass, cudaStream_t stream) {
       if (!make_plane_map(&p.tm[t][3], B.p1, B, ab_batch, b_rows)) return cudaErrorInvalidValue;
     }
   }
-  p.epi_split = epi_split_for(g.t[0].K + (g.nterms > 1 ? g.t[1].K : 0));
+  p.epi_split = epi_split_for(g.t[0].K + (g.nterms > 1 ? g.t[1].K : 0), g.M);
   {
     // 256 ns: -0.5 % Newton-Schulz time against pure spinning (A/B on one box); EGM_EPI_SLEEP_NS overrides
     static unsigned ns = []() { const char* e = getenv("EGM_EPI_SLEEP_NS"); return e ? (unsigned)atoi(e) : 256u; }();
