@@ -315,3 +315,21 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_host_links_and_calls_the_abi(pkg, tmp_path):
+    """tests/native/abi_smoke.c: a C99 program (no C++/CUDA/Python) linked against libegm_b200.so calls
+    the version / size queries and sees argument errors as status codes - the drop-in boundary is a C ABI."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc on this box")
+    lib_dir = os.path.dirname(pkg._lib.lib_path())
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "native", "abi_smoke.c"), "-L", lib_dir, "-legm_b200", "-o", exe],
+                   check=True, capture_output=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=lib_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("abi ok"), (r.returncode, r.stdout, r.stderr)
