@@ -833,6 +833,76 @@ mean_center2_kernel(const float* __restrict__ Z, const float* __restrict__ w,
   }
 }
 
+// same, four adjacent columns per thread (16-byte loads, 8-byte packed plane stores) and 16 row groups:
+// d % 4 == 0. More bytes in flight per thread for the same 1536 blocks of 512 threads.
+constexpr int kMc4Cols = 32, kMc4Groups = 16;
+__global__ void __launch_bounds__(kMc4Cols * kMc4Groups)
+mean_center4_kernel(const float* __restrict__ Z, const float* __restrict__ w,
+                    const float* __restrict__ wdiag, int n, int d, float eps, float* __restrict__ t_out,
+                    float* __restrict__ sw_out, float* __restrict__ mu, float* __restrict__ u, WPtr Zc) {
+  extern __shared__ float shw[];  // n weights
+  __shared__ float sh[32];
+  __shared__ float4 part[kMc4Groups][kMc4Cols];
+  const int b = blockIdx.y;
+  float tl = 0.f, sl = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float wi = w[(long long)b * n + i];
+    shw[i] = wi;
+    sl += wi;
+    tl += wdiag[(long long)b * n + i];
+  }
+  const float t = block_sum(tl, sh);
+  const float sw = block_sum(sl, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { t_out[b] = t; sw_out[b] = sw; }
+  const int tx = threadIdx.x % kMc4Cols, g = threadIdx.x / kMc4Cols;
+  const int j = (blockIdx.x * kMc4Cols + tx) * 4;
+  const bool ok = j < d;
+  const float* z = Z + (long long)b * n * d + j;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok)
+    for (int i = g; i < n; i += kMc4Groups) {
+      const float4 v = *reinterpret_cast<const float4*>(z + (long long)i * d);
+      const float wi = shw[i];
+      a.x = fmaf(wi, v.x, a.x); a.y = fmaf(wi, v.y, a.y); a.z = fmaf(wi, v.z, a.z); a.w = fmaf(wi, v.w, a.w);
+    }
+  part[g][tx] = a;
+  __syncthreads();
+  a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < kMc4Groups; ++q) {     // same order in every group: one value of mu
+    const float4 v = part[q][tx];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  __syncthreads();
+  const float inv = 1.f / (t + eps);
+  const float4 m = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  float4 ua = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    if (g == 0) *reinterpret_cast<float4*>(mu + (long long)b * d + j) = m;
+    const long long o = (long long)b * Zc.bs + j;
+    for (int i = g; i < n; i += kMc4Groups) {
+      const float4 v = *reinterpret_cast<const float4*>(z + (long long)i * d);
+      const float4 c = make_float4(v.x - m.x, v.y - m.y, v.z - m.z, v.w - m.w);
+      const float wi = shw[i];
+      ua.x = fmaf(c.x, wi, ua.x); ua.y = fmaf(c.y, wi, ua.y); ua.z = fmaf(c.z, wi, ua.z); ua.w = fmaf(c.w, wi, ua.w);
+      wstore4(Zc, o + (long long)i * Zc.ld, c);
+    }
+  }
+  if (u) {   // kernel-uniform
+    part[g][tx] = ua;
+    __syncthreads();
+    if (g == 0 && ok) {
+      float4 us = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < kMc4Groups; ++q) {
+        const float4 v = part[q][tx];
+        us.x += v.x; us.y += v.y; us.z += v.z; us.w += v.w;
+      }
+      *reinterpret_cast<float4*>(u + (long long)b * d + j) = make_float4(us.x * inv, us.y * inv, us.z * inv, us.w * inv);
+    }
+  }
+}
+
 // ------------------------------------------------------------ trace, dots
 __global__ void trace_scales_kernel(const float* __restrict__ M, int d, float eps, int post_mode,
                                     float* __restrict__ tr, float* __restrict__ inv,
@@ -1286,38 +1356,48 @@ __global__ void pool_bwd_ds_kernel(const float* __restrict__ dW, long long ldW,
   a = warp_sum(a);
   if (lane == 0) ds[(long long)b * n + i] = a;
 }
-// one warp per row: the row's scalars are read once, columns are walked with coalesced accesses
+// A block walks 32 rows of one image (a warp takes 4 of them); the per-token vectors s, dw and
+// ddeg = -0.5 s^3 ds [deg >= eps] are staged in shared memory once per block, so an element costs one
+// global load (dW) and one store.
+constexpr int kDgRows = 32;
 __global__ void __launch_bounds__(256)
 pool_bwd_dG_kernel(const float* __restrict__ dW, long long ldW, const float* __restrict__ dw,
                    const float* __restrict__ dt, const float* __restrict__ s,
                    const float* __restrict__ deg, const float* __restrict__ ds, int n, float eps,
                    int sym, float* __restrict__ dG) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ float shv[];          // s[n], dw[n], ddeg[n]
+  float* ss = shv;
+  float* sdw = shv + n;
+  float* sdd = shv + 2 * n;
   const int b = blockIdx.y;
-  if (i >= n) return;
-  const int lane = threadIdx.x & 31;
-  const float* sb = s + (long long)b * n;
-  const float* dwb = dw + (long long)b * n;
-  const float* degb = deg + (long long)b * n;
-  const float* dsb = ds + (long long)b * n;
-  const float* dWr = dW + ((long long)b * n + i) * ldW;
-  float* out = dG + ((long long)b * n + i) * n;
-  const float si = sb[i], dwi = dwb[i], dtb = dt[b];
-  // s = max(deg,eps)^(-1/2): d s/d deg = -0.5 s^3 where the clamp is inactive (deg >= eps)
-  const float ddeg = (degb[i] >= eps) ? -0.5f * si * si * si * dsb[i] : 0.f;
-  if (sym) {
-    // symmetric graph: return the symmetric part (dG + dG^T)/2 of the reference's gradient, i.e. the
-    // gradient with respect to a symmetric matrix (dW is symmetric here; row terms are averaged)
-    for (int j = lane; j < n; j += 32) {
-      const float sj = sb[j];
-      const float ddegj = (degb[j] >= eps) ? -0.5f * sj * sj * sj * dsb[j] : 0.f;
-      const float dwf = dWr[j] + 0.5f * (dwi + dwb[j]) + (i == j ? dtb : 0.f);
-      out[j] = si * dwf * sj + 0.5f * (ddeg + ddegj);
-    }
-  } else {
-    for (int j = lane; j < n; j += 32) {
-      const float dwf = dWr[j] + dwi + (i == j ? dtb : 0.f);
-      out[j] = si * dwf * sb[j] + ddeg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = s[(long long)b * n + i];
+    ss[i] = si;
+    sdw[i] = dw[(long long)b * n + i];
+    // s = max(deg,eps)^(-1/2): d s/d deg = -0.5 s^3 where the clamp is inactive (deg >= eps)
+    sdd[i] = (deg[(long long)b * n + i] >= eps) ? -0.5f * si * si * si * ds[(long long)b * n + i] : 0.f;
+  }
+  __syncthreads();
+  const float dtb = dt[b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < kDgRows; r += 8) {
+    const int i = blockIdx.x * kDgRows + r;
+    if (i >= n) break;
+    const float* dWr = dW + ((long long)b * n + i) * ldW;
+    float* out = dG + ((long long)b * n + i) * n;
+    const float si = ss[i], dwi = sdw[i], ddeg = sdd[i];
+    if (sym) {
+      // symmetric graph: return the symmetric part (dG + dG^T)/2 of the reference's gradient, i.e. the
+      // gradient with respect to a symmetric matrix (dW is symmetric here; row terms are averaged)
+      for (int j = lane; j < n; j += 32) {
+        const float dwf = dWr[j] + 0.5f * (dwi + sdw[j]) + (i == j ? dtb : 0.f);
+        out[j] = si * dwf * ss[j] + 0.5f * (ddeg + sdd[j]);
+      }
+    } else {
+      for (int j = lane; j < n; j += 32) {
+        const float dwf = dWr[j] + dwi + (i == j ? dtb : 0.f);
+        out[j] = si * dwf * ss[j] + ddeg;
+      }
     }
   }
 }
@@ -1448,7 +1528,13 @@ void mean_center(const float* Z, const float* w, const float* wdiag, int batch, 
   const bool even = d % 2 == 0 && Zc.ld % 2 == 0 && (reinterpret_cast<uintptr_t>(Z) & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(mu) & 7) == 0 && (!u || (reinterpret_cast<uintptr_t>(u) & 7) == 0) &&
                     (reinterpret_cast<uintptr_t>(Zc.base) & 7) == 0;
-  if (even) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool quad = d % 4 == 0 && Zc.ld % 4 == 0 && al16(Z) && al16(mu) && (!u || al16(u)) && al16(Zc.base);
+  if (quad) {
+    dim3 grid((d / 4 + kMc4Cols - 1) / kMc4Cols, batch);
+    mean_center4_kernel<<<grid, kMc4Cols * kMc4Groups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
+                                                                               u, wptr(Zc, prec));
+  } else if (even) {
     dim3 grid((d / 2 + kMcCols - 1) / kMcCols, batch);
     mean_center2_kernel<<<grid, kMcCols * kMcGroups, n * sizeof(float), st>>>(Z, w, wdiag, n, d, eps, t, sw, mu,
                                                                               u, wptr(Zc, prec));
@@ -1572,8 +1658,11 @@ void pool_bwd_ds(const float* dW, long long ldW, const float* dw, const float* d
 void pool_bwd_dG(const float* dW, long long ldW, const float* dw, const float* dt, const float* s,
                  const float* deg, const float* ds, int batch, int n, float eps, int sym, float* dG,
                  cudaStream_t st) {
-  dim3 grid((n + 7) / 8, batch);
-  pool_bwd_dG_kernel<<<grid, 256, 0, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, sym, dG);
+  dim3 grid((n + kDgRows - 1) / kDgRows, batch);
+  const size_t smem = 3 * (size_t)n * sizeof(float);
+  if (smem > 48 * 1024)   // more than 4096 tokens: opt in to the large shared-memory carve-out
+    cudaFuncSetAttribute(pool_bwd_dG_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pool_bwd_dG_kernel<<<grid, 256, smem, st>>>(dW, ldW, dw, dt, s, deg, ds, n, eps, sym, dG);
   note_launch();
 }
 
