@@ -274,6 +274,23 @@ class _MomentLowRankFunction(Function):
         return dZ, dG, None, None, None, None
 
 
+# ---- early hand-over of a parameter gradient produced in the middle of a fused backward ----------
+# dist.GradBuckets registers itself here: the fused head computes dW of its Linear before the whole
+# Newton-Schulz backward inside ONE autograd node, so a post-accumulate hook on the parameter would
+# fire only after the chain. hook(weight_data_ptr, dW) may start an asynchronous all-reduce of dW and
+# return a handle; the operator calls handle.wait() (a stream-side wait) before returning dW.
+_early_grad_hook = None
+
+
+def set_early_grad_hook(fn) -> None:
+    global _early_grad_hook
+    _early_grad_hook = fn
+
+
+def get_early_grad_hook():
+    return _early_grad_hook
+
+
 class _MomentHeadLinearFunction(Function):
     """pool -> iSQRT-COV -> half-vectorise -> Linear, fused (csrc/egm_api.cu egm_mhd_*, or egm_mlr_*
     for the low-rank evaluation): the packed upper triangle of the normalised covariance is
@@ -315,6 +332,7 @@ class _MomentHeadLinearFunction(Function):
                               *([u] if want_u else []))
         ctx.cfg = (int(iters), float(eps), bool(want_u), bool(lowrank), prec, bias is not None, n_out, K,
                    int(flags))
+        ctx.weight_ptr = weight.data_ptr()
         if want_u:
             return y, u
         return y
@@ -346,6 +364,9 @@ class _MomentHeadLinearFunction(Function):
             _lib.check(L.egm_linear_bwd(dy.data_ptr(), lin_state.data_ptr(), B, n_out, K, dv.data_ptr(),
                                         _p(dw), _p(db), prec, ws.data_ptr(), ws.numel(), _stream(dev)),
                        "egm_linear_bwd")
+            # dW is complete as far as the stream is concerned: let the data-parallel reducer start its
+            # all-reduce now, underneath the Newton-Schulz backward enqueued below
+            pending = _early_grad_hook(ctx.weight_ptr, dw) if (_early_grad_hook is not None and need_w) else None
             dot = _empty(B, device=dev, dtype=torch.float32)   # <dO, O> = <dy, y - bias>
             _lib.check(L.egm_rowdot_bias(dy.data_ptr(), y.data_ptr(), _p(bias), B, n_out, dot.data_ptr(),
                                          _stream(dev)), "egm_rowdot_bias")
@@ -363,6 +384,8 @@ class _MomentHeadLinearFunction(Function):
                                          vecs.data_ptr(), mu.data_ptr(), scal.data_ptr(), state.data_ptr(),
                                          B, N, D, iters, eps, flags, dZ.data_ptr(), dG.data_ptr(), prec,
                                          ws.data_ptr(), ws.numel(), _stream(dev)), "egm_mhd_bwd")
+            if pending is not None:
+                pending.wait()       # stream-side: autograd may read dW from here on
         return dZ, dG, dw, db, None, None, None, None, None, None
 
 

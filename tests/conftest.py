@@ -42,6 +42,19 @@ def make_inputs(B, N, D, seed=1234):
     return anchor, positive
 
 
+def make_structured_inputs(B, N, D, seed=1234, rank=16):
+    """Same "structured" generator as tests/golden/make_golden.py."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    s = 0.5 + 1.5 * torch.rand(B, 1, 1, generator=g)
+    m = torch.randn(B, 1, D, generator=g)
+    L = torch.randn(B, N, rank, generator=g)
+    R = torch.randn(B, D, rank, generator=g)
+    anchor = s * (m + torch.bmm(L, R.transpose(1, 2)) + 0.3 * torch.randn(B, N, D, generator=g))
+    positive = anchor + 0.5 * s * torch.randn(B, N, D, generator=g)
+    return anchor, positive
+
+
 def rel_err(x, ref):
     x = np.asarray(x, np.float64)
     ref = np.asarray(ref, np.float64)

@@ -36,12 +36,27 @@ def make_inputs(B, N, D, seed=1234, dtype=torch.float32):
     return anchor.to(dtype), positive.to(dtype)
 
 
+def make_structured_inputs(B, N, D, seed=1234, dtype=torch.float32, rank=16):
+    """SURVEY.md section 8d "structured" generator: per-image scale s_b ~ U(0.5, 2), mean m_b ~ N(0, I_D),
+    rank-16 factors L_b [N,16], R_b [D,16] and 0.3 noise: anchor = s_b (m_b + L_b R_b^T + 0.3 eps). Images
+    differ in scale, mean and covariance, so train-mode BatchNorm sees non-degenerate batch statistics."""
+    g = torch.Generator().manual_seed(seed)
+    s = 0.5 + 1.5 * torch.rand(B, 1, 1, generator=g)
+    m = torch.randn(B, 1, D, generator=g)
+    L = torch.randn(B, N, rank, generator=g)
+    R = torch.randn(B, D, rank, generator=g)
+    anchor = s * (m + torch.bmm(L, R.transpose(1, 2)) + 0.3 * torch.randn(B, N, D, generator=g))
+    positive = anchor + 0.5 * s * torch.randn(B, N, D, generator=g)
+    return anchor.to(dtype), positive.to(dtype)
+
+
 def npf(t):
     return t.detach().cpu().numpy()
 
 
 def run_case(gk, mh, name, B, N, D, P, Q, K, d_out, third, S, similarity="cosine", symmetric=True,
-             dtype=torch.float64, full=True, train_bn=False, adaptive=None, patch_sketch=False):
+             dtype=torch.float64, full=True, train_bn=False, adaptive=None, patch_sketch=False,
+             structured=False):
     torch.manual_seed(0)
     if adaptive:
         gpf = gk.AdaptiveGraphPolynomialFusion(P, Q, similarity=similarity, symmetric_enforce=symmetric,
@@ -60,7 +75,7 @@ def run_case(gk, mh, name, B, N, D, P, Q, K, d_out, third, S, similarity="cosine
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
     head.train(train_bn)
-    anchor, positive = make_inputs(B, N, D, dtype=dtype)
+    anchor, positive = (make_structured_inputs if structured else make_inputs)(B, N, D, dtype=dtype)
     anchor.requires_grad_(True)
     positive.requires_grad_(True)
     G = gpf(anchor, positive)
@@ -222,7 +237,67 @@ def run_align():
     print("align: ok")
 
 
+def run_dropin():
+    """The WHOLE reference model (ego_moment_clevit.py + classifier_head.py + gpf_kernel.py +
+    moment_head.py, unchanged, float64, CPU) on a tiny stand-in backbone: forward, the five losses,
+    backward. The GPU acceptance test runs the same model file on this repo's drop-in modules."""
+    sys.path.insert(0, os.path.dirname(OUT))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from dropin_stub import StubDualStream
+    from baseline import reference_loader as RL
+    Model = RL.load_model_class(StubDualStream, root=REF, native=False, pkgname="egm_golden_model")
+    torch.manual_seed(0)
+    model = Model(num_classes=5, backbone_name="stub", pretrained=False, gpf_degree_p=2, gpf_degree_q=2,
+                  moment_d_out=16, use_third_order=True, isqrt_iterations=3, sketch_dim=64,
+                  classifier_fusion="concat", lambda_triplet=0.6, lambda_align=0.1, margin=0.3, dropout=0.0)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model = model.double().train()
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(77)
+    B = 6
+    anchor = torch.randn(B, 3, 16, 16, generator=g, dtype=torch.float64)
+    positive = anchor + 0.3 * torch.randn(B, 3, 16, 16, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 5, (B,), generator=g)
+    out = model(anchor, positive, labels, return_features=True)
+    feats = out["features"]
+    watch = {"gpf.alpha_coeffs": model.gpf.alpha_coeffs,
+             "backbone.proj.weight": model.backbone.proj.weight,
+             "backbone.cls_token": model.backbone.cls_token,
+             "moment_head.second_net.0.weight": model.moment_head.second_net[0].weight,
+             "moment_head.third_net.0.weight": model.moment_head.third_net[0].weight,
+             "classifier.classifier.0.weight": model.classifier.classifier[0].weight}
+    grads = torch.autograd.grad(out["loss"], list(watch.values()) + [feats["anchor_tokens"], feats["positive_tokens"]])
+    rec = {"anchor": npf(anchor), "positive": npf(positive), "labels": labels.numpy(),
+           "logits": npf(out["logits"]), "logits_anchor": npf(out["logits_anchor"]),
+           "loss": npf(out["loss"]), "fused_graph": npf(feats["fused_graph"]),
+           "moment_features": npf(feats["moment_features"]),
+           "d_anchor_tokens": npf(grads[-2]), "d_positive_tokens": npf(grads[-1])}
+    for k, v in out["loss_dict"].items():
+        rec["loss:" + k] = npf(v)
+    for (k, _), gval in zip(watch.items(), grads):
+        rec["g:" + k] = npf(gval)
+    for k, v in state.items():
+        rec["p:" + k] = npf(v)
+    np.savez_compressed(os.path.join(OUT, "dropin_model.npz"), **rec)
+    print("dropin_model: loss", float(out["loss"]), {k: float(v) for k, v in out["loss_dict"].items()})
+
+
+def run_structured(gk, mh):
+    # BASELINE config-1 shape on the survey's structured inputs, train-mode BatchNorm (VERDICT r1 item 5b)
+    run_case(gk, mh, "cfg1_structured_trainbn", B=8, N=197, D=768, P=3, Q=3, K=5, d_out=256, third=False,
+             S=0, dtype=torch.float32, full=False, train_bn=True, structured=True)
+
+
 def main():
+    if "--dropin" in sys.argv:
+        run_dropin()
+        return
+    if "--structured" in sys.argv:
+        run_structured(load_ref("ref_gpf_kernel", "src/models/gpf_kernel.py"),
+                       load_ref("ref_moment_head", "src/models/moment_head.py"))
+        return
     only_new = "--new" in sys.argv
     if not os.path.isdir(REF):
         sys.exit(f"reference tree not found at {REF}")
@@ -248,7 +323,9 @@ def main():
     run_case(gk, mh, "cfg1_trainbn", B=8, N=197, D=768, P=3, Q=3, K=5, d_out=256, third=False,
              S=0, dtype=torch.float32, full=False, train_bn=True)
     run_new(gk, mh)
+    run_structured(gk, mh)
     run_align()
+    run_dropin()
 
 
 if __name__ == "__main__":

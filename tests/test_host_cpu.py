@@ -272,6 +272,59 @@ def test_sharded_gradients_equal_mean_of_shard_gradients_gloo():
         assert torch.allclose(got, 0.5 * (ga + gb), atol=1e-6)
 
 
+def _gloo_accum_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    load_pkg()
+    d = importlib.import_module("ego-moment-cle-vit_b200.dist")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 2))
+    buckets = d.GradBuckets(net.parameters(), bucket_bytes=64)         # hooks on: overlap mode
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10.0
+    xs = d.shard(x, rank, world)
+    # (1) two backward passes without no_sync(): must raise, not silently mix local and averaged sums
+    net(xs[:2]).sum().backward()
+    raised = False
+    try:
+        net(xs[2:]).sum().backward()
+    except RuntimeError as exc:
+        raised = "no_sync" in str(exc)
+    buckets.reduce()
+    net.zero_grad(set_to_none=True)
+    # (2) accumulation done right: first micro-batch under no_sync(), last one outside, then reduce()
+    with buckets.no_sync():
+        net(xs[:2]).sum().backward()
+    net(xs[2:]).sum().backward()
+    buckets.reduce()
+    q.put((rank, raised, [p_.grad.numpy().copy() for p_ in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_gradient_accumulation_contract_gloo():
+    """a second backward before reduce() used to leave (sum_ranks g1 + local g2)/world
+    in .grad without any error. Now it raises, and no_sync() gives the mean over ranks of the accumulated sum."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_accum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1], "second backward without no_sync() did not raise"
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 2))
+    x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10.0
+    net(x).sum().backward()                                  # sum over all 8 rows = sum of both ranks' sums
+    for got0, got1, p_ in zip(res[0][2], res[1][2], net.parameters()):
+        assert np.array_equal(got0, got1)
+        assert np.allclose(got0, 0.5 * p_.grad.numpy(), atol=1e-6)
+
+
 def test_shard_bounds_cover_batch():
     d = importlib.import_module("ego-moment-cle-vit_b200.dist")
     for B in (1, 7, 8, 256, 257):
@@ -286,22 +339,59 @@ def test_shard_bounds_cover_batch():
 
 
 # ------------------------------------------------------------------------- bench.py contract
-def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line
-    with the metric / config of the native arm, `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+def _run_reference_arm(env_extra):
     import json
     import subprocess
+    env = dict(os.environ, **env_extra)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
-    d = json.loads(lines[0])
+    return json.loads(lines[0])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line
+    with the metric / config of the native arm, `impl`, `cpu_baseline` and a zero-copy `e2e`. It times the
+    reference's own modules when its sources are found, and it uses every host core even when the
+    launcher exported OMP_NUM_THREADS=1 (torchrun does for N>1: round 1's N>1 ratios were void)."""
+    from baseline import reference_loader as RL
+    d = _run_reference_arm({"OMP_NUM_THREADS": "1"})
     assert d["impl"] == "reference" and d["metric"] == "MomentHead+GPF fwd+bwd images/sec"
     assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    want = "reference" if RL.find_reference_root() else "port"
+    assert d["cpu_baseline"]["kind"] == want
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("configs[1]") and d["config"]["tokens"] == 197
+
+
+def test_bench_reference_arm_falls_back_to_the_port(tmp_path, monkeypatch):
+    """With no reference sources anywhere the CPU arm is the oracle port and says so."""
+    import bench
+    from baseline import reference_loader as RL
+    monkeypatch.setattr(RL, "find_reference_root", lambda: None)
+    monkeypatch.setattr(bench, "N_TOK", 24)
+    monkeypatch.setattr(bench, "D_IN", 32)
+    ref = bench.CpuReferenceStep()
+    assert ref.kind == "port" and "port" in ref.where
+    ref(2)
+
+
+def test_reference_install_is_verbatim():
+    """baseline/_ref (git-ignored, travels to the GPU box) holds the reference's files unmodified."""
+    from baseline import reference_loader as RL
+    if not os.path.isdir(RL.INSTALL_DIR):
+        pytest.skip("no reference install on this box")
+    assert RL.verify_install()
+    if os.path.isdir(REF):
+        import filecmp
+        for name in ("gpf_kernel.py", "moment_head.py", "ego_moment_clevit.py", "classifier_head.py"):
+            assert filecmp.cmp(os.path.join(REF, "src", "models", name),
+                               os.path.join(RL.INSTALL_DIR, "src", "models", name), shallow=False)
+    gk, mh, ops = RL.load_path_modules(RL.INSTALL_DIR, pkgname="egm_ref_install_probe")
+    assert hasattr(gk, "GraphPolynomialFusion") and hasattr(mh, "MomentHead") and hasattr(ops, "batch_trace")
 
 
 def test_header_is_plain_c():
