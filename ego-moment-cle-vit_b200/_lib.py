@@ -37,6 +37,7 @@ SIGNATURES = {
     "egm_prof_reset": (None, []),
     "egm_prof_count": (_I, []),
     "egm_prof_read": (_I, [_I, _P, _P, _P]),
+    "egm_gpf_fused_ok": (_I, [_I, _I, _I, _I, _I]),
     "egm_gpf_ldr": (_LL, [_I]),
     "egm_gpf_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_gpf_state_bytes": (_Z, [_I, _I, _I, _I]),
@@ -80,6 +81,8 @@ SIGNATURES = {
     "egm_gram_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _Z, _P]),
     "egm_normalize_graph": (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
     "egm_batch_trace": (_I, [_P, _I, _I, _P, _P]),
+    "egm_feature_tail_fwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _F, _F, _F, ctypes.c_ulonglong, _P, _P, _P, _P]),
+    "egm_feature_tail_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, ctypes.c_ulonglong, _P, _P, _P, _P]),
     "egm_bmm_workspace": (_Z, [_I, _I, _I, _I, _I]),
     "egm_bmm": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P, _Z, _P]),
 }

@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libegm_b200.so")
-SOURCES = ["egm_api.cu", "egm_lowrank.cu", "egm_gemm_tc.cu", "egm_gemm_simt.cu", "egm_kernels.cu", "egm_error.cu"]
+SOURCES = ["egm_api.cu", "egm_lowrank.cu", "egm_gemm_tc.cu", "egm_gemm_simt.cu", "egm_kernels.cu", "egm_gpf_fused.cu",
+           "egm_error.cu"]
 HEADERS = ["egm_gemm.h", "egm_chain.h", "egm_kernels.cuh", "egm_ptx.cuh", os.path.join("..", "..", "include", "egm_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
          "-shared", "-Xcompiler", "-fPIC"]

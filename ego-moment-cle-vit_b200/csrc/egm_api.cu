@@ -328,17 +328,33 @@ size_t egm_gpf_state_bytes(int B, int N, int D, int prec) {
   return 2 * pad256(w_bytes(B, N, D)) + 256;
 }
 
+int egm_gpf_fused_ok(int N, int D, int P, int Q, int prec) {
+  static const float dummy[4] __attribute__((aligned(16))) = {0.f, 0.f, 0.f, 0.f};
+  return prec != PREC_FP32_SIMT && k::gpf_fused_supported(N, D, P, Q, dummy, dummy) ? 1 : 0;
+}
+
 int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
                 int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
                 float* nrm_p, void* xn_state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_fwd: unknown precision mode %d", prec);
+  EGM_REQUIRE(a && p && coef && G && nrm_a && nrm_p, EGM_ERR_ARG, "egm_gpf_fwd: null pointer");
+  EGM_REQUIRE((Ra == nullptr) == (Rp == nullptr), EGM_ERR_ARG, "egm_gpf_fwd: Ra and Rp go together");
+  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && P >= 0 && Q >= 0 && P <= 15 && Q <= 15, EGM_ERR_ARG,
+              "egm_gpf_fwd: bad sizes B=%d N=%d D=%d P=%d Q=%d (degrees 0..15)", B, N, D, P, Q);
+  // One fused pass (egm_gpf_fused.cu) whenever the tensor-core modes can address the tokens: nothing
+  // but G, the norms and (on request) R_a / R_p is written; the normalised operand planes are not
+  // produced (xn_state stays unused and the backward re-derives them).
+  if (prec != PREC_FP32_SIMT && !xn_state && k::gpf_fused_supported(N, D, P, Q, a, p)) {
+    (void)symmetric;   // the fused result is symmetric by construction: F_ij is evaluated once per pair
+    EGM_CUDA(k::gpf_fused_fwd(a, p, coef, B, N, D, P, Q, cosine, eps, G, Ra, Rp, egm_gpf_ldr(N), nrm_a,
+                              nrm_p, prec == PREC_BF16X3 ? 3 : 1, st));
+    return EGM_OK;
+  }
+  EGM_REQUIRE(Ra && Rp, EGM_ERR_ARG, "egm_gpf_fwd: the staged path needs Ra and Rp");
   // the normalised tokens (GEMM operand planes) go to `xn_state` when the caller keeps them for the
   // backward, else to scratch
   if (xn_state) { ws = xn_state; ws_bytes = egm_gpf_state_bytes(B, N, D, prec); }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  EGM_REQUIRE(prec_ok(prec), EGM_ERR_ARG, "egm_gpf_fwd: unknown precision mode %d", prec);
-  EGM_REQUIRE(a && p && coef && G && Ra && Rp && nrm_a && nrm_p, EGM_ERR_ARG, "egm_gpf_fwd: null pointer");
-  EGM_REQUIRE(B > 0 && N > 0 && D > 0 && P >= 0 && Q >= 0 && P <= 15 && Q <= 15, EGM_ERR_ARG,
-              "egm_gpf_fwd: bad sizes B=%d N=%d D=%d P=%d Q=%d (degrees 0..15)", B, N, D, P, Q);
   Arena ar(ws, ws_bytes);
   void* wa = ar.take(w_bytes(B, N, D));
   void* wp = ar.take(w_bytes(B, N, D));
@@ -1014,6 +1030,34 @@ int egm_linear_bwd(const float* dy, const void* state, int M, int N, int K, floa
     k::colsum(dy, M, N, dbias, st);
     EGM_LAUNCHED();
   }
+  return EGM_OK;
+}
+
+// ============================================================ feature-net tail (BN + GELU + Dropout)
+int egm_feature_tail_fwd(const float* y, int M, int N, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int training, float momentum, float bn_eps,
+                         float drop_p, unsigned long long seed, float* out, float* save_mean, float* save_rstd,
+                         egm_stream_t stream) {
+  EGM_REQUIRE(y && out && save_mean && save_rstd && M > 0 && N > 0, EGM_ERR_ARG, "egm_feature_tail_fwd: bad argument");
+  EGM_REQUIRE(training || (running_mean && running_var), EGM_ERR_ARG,
+              "egm_feature_tail_fwd: eval mode needs the running statistics");
+  EGM_REQUIRE((running_mean == nullptr) == (running_var == nullptr), EGM_ERR_ARG,
+              "egm_feature_tail_fwd: running_mean and running_var go together");
+  EGM_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, EGM_ERR_ARG, "egm_feature_tail_fwd: dropout p=%f", (double)drop_p);
+  k::feature_tail_fwd(y, M, N, gamma, beta, running_mean, running_var, training, momentum, bn_eps, drop_p, seed,
+                      out, save_mean, save_rstd, static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
+  return EGM_OK;
+}
+int egm_feature_tail_bwd(const float* dout, const float* y, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_rstd, int M, int N, int training,
+                         float drop_p, unsigned long long seed, float* dy, float* dgamma, float* dbeta,
+                         egm_stream_t stream) {
+  EGM_REQUIRE(dout && y && save_mean && save_rstd && dy && M > 0 && N > 0, EGM_ERR_ARG,
+              "egm_feature_tail_bwd: bad argument");
+  k::feature_tail_bwd(dout, y, M, N, gamma, beta, save_mean, save_rstd, training, drop_p, seed, dy, dgamma, dbeta,
+                      static_cast<cudaStream_t>(stream));
+  EGM_LAUNCHED();
   return EGM_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/egm_b200.h"
 #include "egm_gemm.h"
@@ -55,7 +56,9 @@ inline GemmTerm term(const W& A, int tA, const W& B, int tB, int K, int prec) {
   do {                                                                              \
     cudaError_t e_ = (expr);                                                        \
     if (e_ != cudaSuccess) {                                                        \
-      set_error("%s: %s [%s]", #expr, cudaGetErrorString(e_), last_error());        \
+      char prev_[256];                /* set_error formats INTO the buffer last_error() returns */ \
+      snprintf(prev_, sizeof(prev_), "%s", last_error());                           \
+      set_error("%s: %s [%s]", #expr, cudaGetErrorString(e_), prev_);               \
       return EGM_ERR_CUDA;                                                          \
     }                                                                               \
   } while (0)

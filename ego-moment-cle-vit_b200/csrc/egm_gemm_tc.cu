@@ -62,6 +62,7 @@ struct alignas(64) TcParams {
   int tma_cp, tma_cf, tma_c2;  // which outputs leave through TMA stores
   int epi_split;         // hi and lo plane stores of a chunk as separate bulk groups
   unsigned epi_sleep_ns; // back-off of the epilogue warps while they wait for an accumulator
+  unsigned* sched;       // dynamic tile scheduler: [0] next tile, [1] clusters done (self-resetting)
   int splits;            // split-K: `batch` counts K-slices of ONE problem (A/B batch index 0)
   int M, N, batch, nterms;
   int K[2], a_mn[2], b_mn[2];
@@ -452,6 +453,20 @@ __global__ void dot_reduce_kernel(const float* __restrict__ ws, int per_img, int
 // this kernel measured 1155 TFLOP/s executed against 1334 for the pair in round 1 and was retired.)
 constexpr int kTileBh = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the B tile
 
+// Dynamic tile scheduler. Tiles are handed out by an atomic counter in global memory instead of the
+// static `tile += nclusters` walk, so a CTA pair that starts late (its SMs were held by another
+// kernel - NCCL's all-reduce CTAs under the Newton-Schulz backward in data-parallel training) simply
+// takes fewer tiles instead of becoming the tail of every launch. The leader CTA's producer warp
+// fetches the next tile index and publishes it through a small ring in the shared memory of BOTH
+// CTAs (plain stores + cluster-scope release/acquire mbarriers); the peer's producer, the MMA warp
+// and the 16 epilogue warps each read it and free the slot. -1 ends every role's loop.
+// The counter pair of a launch is one slot of a device-global pool picked round-robin on the host;
+// the last pair to finish zeroes it, so a slot is clean long before it comes round again.
+constexpr int kSched = 4;                          // ring depth (tiles the producer may run ahead)
+constexpr int kSchedReaders = 2 * kEpiWarps + 2;   // leader: MMA + 8 epilogue; peer: producer + 8 epilogue
+constexpr int kSchedPool = 4096;
+__device__ unsigned g_sched_pool[kSchedPool][2];
+
 template <int NPASS>
 struct Cfg2 {
   static constexpr int kPlanes = (NPASS == 3) ? 2 : 1;
@@ -473,6 +488,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  auto sfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 5 + s); };
+  auto sempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 5 + kSched + s); };
+  const uint32_t stile = bar_base + 8u * (2 * C::kStages + 5 + 2 * kSched);   // kSched x int
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
       smem_gen + C::kStages * C::kStageBytes + kEpiBytes + 8 * (2 * C::kStages + 4));
@@ -482,13 +500,21 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = (rank == 0);
 
+  // The launch's counter slot is untouched since the kernel that last used it zeroed it (kSchedPool
+  // launches ago), so the first fetch may run before griddep_wait(), under the previous kernel's tail.
+  int next_fetch = 0;
   if (warp == 0 && lane == 0) {
+    if (leader) next_fetch = p.sched ? (int)atomicAdd(p.sched, 1u) : (int)(blockIdx.x >> 1);
     for (int t = 0; t < p.nterms; ++t)
       for (int i = 0; i < 4; ++i)
         if (i % 2 == 0 || NPASS == 3) ptx::prefetch_tensormap(&p.tm[t][i]);
   }
   if (warp == 1) {
     if (lane == 0) {
+      for (int s = 0; s < kSched; ++s) {
+        ptx::mbar_init(sfull_bar(s), 1);                 // the leader's producer publishes
+        ptx::mbar_init(sempty_bar(s), kSchedReaders);    // used in the leader: every reader of both CTAs
+      }
       for (int s = 0; s < C::kStages; ++s) {
         ptx::mbar_init(full_bar(s), 1);    // used in the leader: its own arrive.expect_tx
         ptx::mbar_init(empty_bar(s), 1);   // multicast commit of the leader's MMA warp
@@ -514,8 +540,16 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
 
   const int tiles_per_img = p.tiles_per_img;             // tiles_m counts 256-row tiles here
   const int ntiles = tiles_per_img * p.batch;
-  const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
+  // a reader's side of the ring: wait for slot `it`, read the tile index, free the slot (in the leader)
+  auto next_tile = [&](int it, uint32_t sleep_ns) -> int {
+    const int s = it % kSched;
+    ptx::mbar_wait_cluster(sfull_bar(s), (uint32_t)(it / kSched) & 1u, sleep_ns);
+    const int t = (int)ptx::ld_shared_u32(stile + 4u * s);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_release_cluster(ptx::mapa(sempty_bar(s), 0));
+    return t;
+  };
 
   if (warp == 0) {
     // --------------------------------------------- TMA producer (both CTAs of the pair)
@@ -524,7 +558,29 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       const bool issuer = ptx::elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+      for (int it = 0;; ++it) {
+        int tile;
+        if (leader) {
+          // the scheduler: fetch, publish to both CTAs' rings
+          const int s = it % kSched;
+          ptx::mbar_wait_cluster(sempty_bar(s), ((uint32_t)(it / kSched) & 1u) ^ 1u);
+          tile = 0;
+          if (lane == 0) {
+            // the index fetched one tile ago; the fetch for the tile after this one goes out now and its
+            // latency hides under this tile's loads (p.sched == nullptr: the static walk, for A/B runs)
+            tile = next_fetch;
+            if (tile >= ntiles) tile = -1;
+            else next_fetch = p.sched ? (int)atomicAdd(p.sched, 1u) : tile + nclusters;
+            ptx::st_shared_cluster_u32(ptx::mapa(stile + 4u * s, 0), (uint32_t)tile);
+            ptx::st_shared_cluster_u32(ptx::mapa(stile + 4u * s, 1), (uint32_t)tile);
+            ptx::mbar_arrive_release_cluster(ptx::mapa(sfull_bar(s), 0));
+            ptx::mbar_arrive_release_cluster(ptx::mapa(sfull_bar(s), 1));
+          }
+          tile = __shfl_sync(0xffffffffu, tile, 0);
+        } else {
+          tile = next_tile(it, 0);
+        }
+        if (tile < 0) break;
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         int tm, tn;
@@ -586,7 +642,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+      for (int it = 0;; ++it) {
+        const int tile = next_tile(it, 0);
+        if (tile < 0) break;
         const int bt = tile / tiles_per_img;
         int tm, tn;
         tile_coords(p, tile - bt * tiles_per_img, tm, tn);
@@ -650,7 +708,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     int half_slot = 0;                  // persists across tiles: a store may still be in flight
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+    for (int it = 0;; ++it) {
+      const int tile = next_tile(it, p.epi_sleep_ns);
+      if (tile < 0) break;
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
       int tm, tn;
@@ -681,6 +741,13 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+  if (leader && threadIdx.x == 0 && p.sched) {
+    // this pair has seen the end of the tile list; the last pair leaves the slot clean for its next user
+    if (atomicAdd(p.sched + 1, 1u) == (unsigned)nclusters - 1u) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+    }
   }
 }
 
@@ -778,6 +845,21 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured_dev = dev;
   }
+  // one counter pair of the device-global pool per launch, round-robin (see g_sched_pool)
+  static thread_local unsigned* pool = nullptr;
+  static thread_local int pool_dev = -1;
+  static thread_local unsigned seq = 0;
+  if (pool_dev != dev) {
+    void* sym = nullptr;
+    e = cudaGetSymbolAddress(&sym, g_sched_pool);
+    if (e != cudaSuccess) return e;
+    pool = static_cast<unsigned*>(sym);
+    pool_dev = dev;
+  }
+  // EGM_SCHED=0: static round-robin tiles (A/B switch)
+  static const bool dynamic = []() { const char* e = getenv("EGM_SCHED"); return !(e && e[0] == '0'); }();
+  TcParams q = p;
+  q.sched = dynamic ? pool + 2u * ((seq++) % (unsigned)kSchedPool) : nullptr;
   int sms = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
@@ -794,7 +876,7 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<NPASS>, p);
+  e = cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<NPASS>, q);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

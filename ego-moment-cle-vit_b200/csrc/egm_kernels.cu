@@ -1273,6 +1273,116 @@ __global__ void colsum_kernel(const float* __restrict__ x, int m, int n, float* 
   out[j] = a;
 }
 
+// ------------------------------------------------- BatchNorm1d -> GELU -> Dropout (feature nets)
+// second_net / third_net after their Linear (moment_head.py:186-191,195-200): BatchNorm1d (train: batch
+// statistics, biased variance for the normalisation, unbiased for the running update, momentum 0.1;
+// eval: running statistics), exact (erf) GELU, inverted Dropout. One block owns 32 features for all
+// rows, so the per-feature reductions never leave the block: deterministic, one launch each way.
+constexpr int kFtCols = 32, kFtRows = 32;
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_f(float z) {
+  return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * __expf(-0.5f * z * z) * 0.39894228040143268f;
+}
+// keep-mask of inverted dropout: a counter-based hash of (seed, element index) -> uniform [0,1)
+__device__ __forceinline__ float drop_scale(unsigned long long seed, long long idx, float p, float inv_keep) {
+  if (p <= 0.f) return 1.f;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.f / 16777216.f);
+  return u >= p ? inv_keep : 0.f;
+}
+// column sums over the block's rows: sh[kFtRows][kFtCols]; result in every thread of the column
+__device__ __forceinline__ float ft_colsum(float v, float (*sh)[kFtCols], int tx, int ty) {
+  __syncthreads();
+  sh[ty][tx] = v;
+  __syncthreads();
+  float a = 0.f;
+#pragma unroll
+  for (int r = 0; r < kFtRows; ++r) a += sh[r][tx];
+  return a;
+}
+__global__ void __launch_bounds__(kFtCols * kFtRows)
+feature_tail_fwd_kernel(const float* __restrict__ y, int m, int n, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ run_mean,
+                        float* __restrict__ run_var, int training, float momentum, float bn_eps, float drop_p,
+                        unsigned long long seed, float* __restrict__ out, float* __restrict__ save_mean,
+                        float* __restrict__ save_rstd) {
+  __shared__ float sh[kFtRows][kFtCols];
+  const int tx = threadIdx.x & (kFtCols - 1), ty = threadIdx.x / kFtCols;
+  const int j = blockIdx.x * kFtCols + tx;
+  const bool ok = j < n;
+  float mean, rstd;
+  if (training) {
+    float a = 0.f;
+    for (int i = ty; i < m; i += kFtRows) a += ok ? y[(long long)i * n + j] : 0.f;
+    mean = ft_colsum(a, sh, tx, ty) / (float)m;
+    float v = 0.f;
+    for (int i = ty; i < m; i += kFtRows) {
+      const float d = ok ? y[(long long)i * n + j] - mean : 0.f;
+      v = fmaf(d, d, v);
+    }
+    const float var = ft_colsum(v, sh, tx, ty) / (float)m;
+    rstd = rsqrtf(var + bn_eps);
+    if (ok && ty == 0 && run_mean) {
+      run_mean[j] = (1.f - momentum) * run_mean[j] + momentum * mean;
+      run_var[j] = (1.f - momentum) * run_var[j] + momentum * var * ((float)m / (float)(m > 1 ? m - 1 : 1));
+    }
+  } else {
+    mean = ok ? run_mean[j] : 0.f;
+    rstd = ok ? rsqrtf(run_var[j] + bn_eps) : 0.f;
+  }
+  if (ok && ty == 0) { save_mean[j] = mean; save_rstd[j] = rstd; }
+  if (!ok) return;
+  const float g = gamma ? gamma[j] : 1.f, bt = beta ? beta[j] : 0.f;
+  const float inv_keep = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
+  for (int i = ty; i < m; i += kFtRows) {
+    const long long o = (long long)i * n + j;
+    const float z = (y[o] - mean) * rstd * g + bt;
+    out[o] = gelu_f(z) * (training ? drop_scale(seed, o, drop_p, inv_keep) : 1.f);
+  }
+}
+__global__ void __launch_bounds__(kFtCols * kFtRows)
+feature_tail_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, int m, int n,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                        int training, float drop_p, unsigned long long seed, float* __restrict__ dy,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sh[kFtRows][kFtCols];
+  const int tx = threadIdx.x & (kFtCols - 1), ty = threadIdx.x / kFtCols;
+  const int j = blockIdx.x * kFtCols + tx;
+  const bool ok = j < n;
+  const float mean = ok ? save_mean[j] : 0.f, rstd = ok ? save_rstd[j] : 0.f;
+  const float g = (ok && gamma) ? gamma[j] : 1.f, bt = (ok && beta) ? beta[j] : 0.f;
+  const float inv_keep = drop_p < 1.f ? 1.f / (1.f - drop_p) : 0.f;
+  // dz = dout * mask * gelu'(z);  dbeta = sum dz;  dgamma = sum dz * xhat
+  float sb = 0.f, sg = 0.f;
+  for (int i = ty; i < m; i += kFtRows) {
+    if (!ok) break;
+    const long long o = (long long)i * n + j;
+    const float xh = (y[o] - mean) * rstd;
+    const float dz = dout[o] * (training ? drop_scale(seed, o, drop_p, inv_keep) : 1.f) * dgelu_f(xh * g + bt);
+    sb += dz;
+    sg = fmaf(dz, xh, sg);
+  }
+  const float db = ft_colsum(sb, sh, tx, ty);
+  const float dg = ft_colsum(sg, sh, tx, ty);
+  if (ok && ty == 0) {
+    if (dbeta) dbeta[j] = db;
+    if (dgamma) dgamma[j] = dg;
+  }
+  if (!ok) return;
+  const float inv_m = 1.f / (float)m;
+  for (int i = ty; i < m; i += kFtRows) {
+    const long long o = (long long)i * n + j;
+    const float xh = (y[o] - mean) * rstd;
+    const float dz = dout[o] * (training ? drop_scale(seed, o, drop_p, inv_keep) : 1.f) * dgelu_f(xh * g + bt);
+    // train: d xhat = g dz; dy = rstd (d xhat - mean(d xhat) - xhat mean(d xhat xhat)); eval: constants
+    dy[o] = training ? rstd * g * (dz - db * inv_m - xh * dg * inv_m) : dz * g * rstd;
+  }
+}
+
 // ---------------------------------------------------------- pooling backward
 __global__ void __launch_bounds__(128)
 pool_bwd_dmu_kernel(const float* __restrict__ dZc, const float* __restrict__ du,
@@ -1628,6 +1738,20 @@ void reduce_splits(const float* partial, int splits, int m, int n, const float* 
                    cudaStream_t st) {
   const long long mn = (long long)m * n;
   reduce_splits_kernel<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(partial, splits, mn, n, bias, y);
+  note_launch();
+}
+void feature_tail_fwd(const float* y, int m, int n, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, int training, float momentum, float bn_eps, float drop_p,
+                      unsigned long long seed, float* out, float* save_mean, float* save_rstd, cudaStream_t st) {
+  feature_tail_fwd_kernel<<<(n + kFtCols - 1) / kFtCols, kFtCols * kFtRows, 0, st>>>(
+      y, m, n, gamma, beta, run_mean, run_var, training, momentum, bn_eps, drop_p, seed, out, save_mean, save_rstd);
+  note_launch();
+}
+void feature_tail_bwd(const float* dout, const float* y, int m, int n, const float* gamma, const float* beta,
+                      const float* save_mean, const float* save_rstd, int training, float drop_p,
+                      unsigned long long seed, float* dy, float* dgamma, float* dbeta, cudaStream_t st) {
+  feature_tail_bwd_kernel<<<(n + kFtCols - 1) / kFtCols, kFtCols * kFtRows, 0, st>>>(
+      dout, y, m, n, gamma, beta, save_mean, save_rstd, training, drop_p, seed, dy, dgamma, dbeta);
   note_launch();
 }
 void colsum(const float* x, int m, int n, float* out, cudaStream_t st) {

@@ -69,6 +69,14 @@ void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long l
                   cudaStream_t st);
 int gpf_poly_bwd_blocks(int batch, int n);
 
+// GraphPolynomialFusion.forward in one pass over the tokens (egm_gpf_fused.cu): Gram matrices of both
+// views on tcgen05 from fp32 tokens converted on the fly, cosine scaling + polynomial + clamp in the
+// epilogue. Ra / Rp (optional, [B][n][ldR]) are written when the backward will need them.
+bool gpf_fused_supported(int n, int d, int P, int Q, const float* a, const float* p);
+cudaError_t gpf_fused_fwd(const float* a, const float* p, const float* coef, int batch, int n, int d, int P,
+                          int Q, int cosine, float eps, float* G, float* Ra, float* Rp, long long ldR,
+                          float* nrm_a, float* nrm_p, int npass, cudaStream_t st);
+
 // deg = G 1 ; s = rsqrt(max(deg, eps))
 void degree(const float* G, int batch, int n, float eps, float* deg, float* s, cudaStream_t st);
 // Wn_ij = s_i G_ij s_j (working matrix) ; w = Wn 1 ; wdiag_i = Wn_ii
@@ -121,6 +129,15 @@ void mlr_scalars_bwd(const float* scal, int batch, float aK, const float* dotOO,
 void reduce_splits(const float* partial, int splits, int m, int n, const float* bias, float* y,
                    cudaStream_t st);
 void colsum(const float* x, int m, int n, float* out, cudaStream_t st);   // out[n] = sum_m x[m,n]
+// BatchNorm1d -> GELU(erf) -> Dropout after a feature net's Linear (moment_head.py:186-191,195-200):
+// y [m,n] is the Linear's output; training: batch statistics (and the running-stat update when
+// run_mean / run_var are given), eval: running statistics. save_mean / save_rstd [n] feed the backward.
+void feature_tail_fwd(const float* y, int m, int n, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, int training, float momentum, float bn_eps, float drop_p,
+                      unsigned long long seed, float* out, float* save_mean, float* save_rstd, cudaStream_t st);
+void feature_tail_bwd(const float* dout, const float* y, int m, int n, const float* gamma, const float* beta,
+                      const float* save_mean, const float* save_rstd, int training, float drop_p,
+                      unsigned long long seed, float* dy, float* dgamma, float* dbeta, cudaStream_t st);
 
 // ---- fused moment head (pool -> iSQRT-COV -> packed half-vector as the Linear's operand)
 // out = s_b[b] * unpack(dv[b, :L]) as a D x D working matrix, zero lower triangle;

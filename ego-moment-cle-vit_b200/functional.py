@@ -114,22 +114,28 @@ class _GPFFunction(Function):
         P, Q = coef.shape[0] - 1, coef.shape[1] - 1
         dev = a.device
         ldr = L.egm_gpf_ldr(N)
+        need_grad = any(ctx.needs_input_grad[:3])
+        # one fused pass over the tokens when the library can address them (egm_gpf_fused_ok): it never
+        # writes the normalised tokens, and writes R_a / R_p only when a backward will read them
+        fused = bool(L.egm_gpf_fused_ok(N, D, P, Q, prec)) and a.data_ptr() % 16 == 0 and p.data_ptr() % 16 == 0
         with torch.cuda.device(dev):
             G = _empty(B, N, N, device=dev, dtype=torch.float32)
-            Ra = _empty(B, N, ldr, device=dev, dtype=torch.float32)
-            Rp = _empty(B, N, ldr, device=dev, dtype=torch.float32)
+            want_R = need_grad or not fused
+            Ra = _empty(B, N, ldr, device=dev, dtype=torch.float32) if want_R else None
+            Rp = _empty(B, N, ldr, device=dev, dtype=torch.float32) if want_R else None
             nrm = _empty(2, B, N, device=dev, dtype=torch.float32)
             coef_c = coef.detach().contiguous()
-            # keep the normalised tokens (GEMM operand planes, 2 x [B,N,D]) for the backward when one
-            # will run; EGM_GPF_RECOMPUTE=1 trades them for a re-normalisation pass in the backward
-            keep = any(ctx.needs_input_grad[:3]) and not _gpf_recompute
+            # staged path: keep the normalised tokens (GEMM operand planes, 2 x [B,N,D]) for the backward
+            # when one will run; EGM_GPF_RECOMPUTE=1 trades them for a re-normalisation pass in the backward
+            keep = need_grad and not _gpf_recompute and not fused
             xn = _ws(L.egm_gpf_state_bytes(B, N, D, prec), dev) if keep else None
-            ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec) if not keep else 16, dev)
+            ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec) if not (keep or fused) else 16, dev)
             _lib.check(L.egm_gpf_fwd(a.data_ptr(), p.data_ptr(), coef_c.data_ptr(), B, N, D, P, Q,
                                      int(cosine), float(eps), int(symmetric), G.data_ptr(),
-                                     Ra.data_ptr(), Rp.data_ptr(), nrm[0].data_ptr(), nrm[1].data_ptr(),
+                                     _p(Ra), _p(Rp), nrm[0].data_ptr(), nrm[1].data_ptr(),
                                      _p(xn), prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_gpf_fwd")
-        ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm, *([xn] if keep else []))
+        if need_grad:
+            ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm, *([xn] if keep else []))
         ctx.cfg = (int(cosine), float(eps), int(symmetric), prec)
         return G
 
@@ -574,18 +580,141 @@ class _LinearFunction(Function):
         return dx, dw, db, None
 
 
+class _LinearSimtFunction(Function):
+    """F.linear in the strict fp32 mode: three products on the library's FFMA engine (egm_bmm)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = bmm(x.unsqueeze(0), weight.unsqueeze(0), trans_b=True, precision="fp32_simt").squeeze(0)
+        if bias is not None:
+            y += bias
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = bmm(dy.unsqueeze(0), weight.unsqueeze(0), precision="fp32_simt").squeeze(0)
+        if ctx.needs_input_grad[1]:
+            dw = bmm(dy.unsqueeze(0), x.unsqueeze(0), trans_a=True, precision="fp32_simt").squeeze(0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
 def linear(x, weight, bias=None, *, precision=None):
-    """F.linear(x, weight, bias) for 2-D x on the tcgen05 engine (split-K over all CTA pairs).
-    In the strict 'fp32_simt' mode this plain GEMM is left to torch (cuBLAS fp32)."""
+    """F.linear(x, weight, bias) for 2-D x on the tcgen05 engine (split-K over all CTA pairs); in the
+    strict 'fp32_simt' mode on the library's FFMA engine (egm_bmm). Never a torch / cuBLAS GEMM."""
     prec = _prec(precision)
     if prec == _lib.PREC_FP32_SIMT:
-        return torch.nn.functional.linear(x, weight, bias)
+        x = _require_cuda_f32("x", x, 2)
+        w = _require_cuda_f32("weight", weight, 2)
+        if w.shape[1] != x.shape[1]:
+            raise RuntimeError(f"linear: x {tuple(x.shape)} and weight {tuple(w.shape)} do not match")
+        b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
+        return _LinearSimtFunction.apply(x, w, b)
     x = _require_cuda_f32("x", x, 2)
     w = _require_cuda_f32("weight", weight, 2)
     if w.shape[1] != x.shape[1]:
         raise RuntimeError(f"linear: x {tuple(x.shape)} and weight {tuple(w.shape)} do not match")
     b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
     return _LinearFunction.apply(x, w, b, prec)
+
+
+# ------------------------------------------------------- BatchNorm1d + GELU + Dropout
+class _FeatureTailFunction(Function):
+    @staticmethod
+    def forward(ctx, y, gamma, beta, run_mean, run_var, training, momentum, bn_eps, drop_p, seed):
+        L = _lib.load()
+        M, N = y.shape
+        dev = y.device
+        with torch.cuda.device(dev):
+            out = _empty_like(y)
+            stats = _empty(2, N, device=dev, dtype=torch.float32)
+            _lib.check(L.egm_feature_tail_fwd(y.data_ptr(), M, N, _p(gamma), _p(beta), _p(run_mean), _p(run_var),
+                                              int(training), float(momentum), float(bn_eps), float(drop_p),
+                                              int(seed), out.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                              _stream(dev)), "egm_feature_tail_fwd")
+        ctx.save_for_backward(y, stats, *([gamma] if gamma is not None else []),
+                              *([beta] if beta is not None else []))
+        ctx.cfg = (int(training), float(drop_p), int(seed), gamma is not None, beta is not None)
+        ctx.mark_non_differentiable(*[t for t in (run_mean, run_var) if t is not None])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        L = _lib.load()
+        training, drop_p, seed, has_g, has_b = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        y, stats = saved[:2]
+        rest = saved[2:]
+        gamma = rest.pop(0) if has_g else None
+        beta = rest.pop(0) if has_b else None
+        M, N = y.shape
+        dev = y.device
+        dout = dout.contiguous()
+        with torch.cuda.device(dev):
+            dy = _empty_like(y)
+            dgamma = _empty(N, device=dev, dtype=torch.float32) if has_g else None
+            dbeta = _empty(N, device=dev, dtype=torch.float32) if has_b else None
+            _lib.check(L.egm_feature_tail_bwd(dout.data_ptr(), y.data_ptr(), _p(gamma), _p(beta), stats[0].data_ptr(),
+                                              stats[1].data_ptr(), M, N, training, drop_p, seed, dy.data_ptr(),
+                                              _p(dgamma), _p(dbeta), _stream(dev)), "egm_feature_tail_bwd")
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def _draw_seed() -> int:
+    """A 63-bit dropout seed from torch's default CPU generator: host-side, no launch, no sync, and
+    reproducible under torch.manual_seed."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def feature_tail(y, layers):
+    """The layers after a feature net's Linear - BatchNorm1d -> GELU -> Dropout (moment_head.py:186-191,
+    195-200) - as one kernel each way. `layers` are the nn.Modules themselves: their parameters,
+    running statistics (updated in place like nn.BatchNorm1d, incl. num_batches_tracked) and
+    train/eval flags are used as they are, so state_dicts are unaffected. The dropout keep-mask comes
+    from a counter-based hash seeded from torch's CPU generator, not from torch's CUDA Philox stream:
+    same distribution, different bits. Any other layer combination is applied layer by layer."""
+    layers = list(layers)
+    nn = torch.nn
+    if not (len(layers) == 3 and isinstance(layers[0], nn.BatchNorm1d) and isinstance(layers[1], nn.GELU)
+            and getattr(layers[1], "approximate", "none") == "none" and isinstance(layers[2], nn.Dropout)
+            and y.dim() == 2 and y.is_cuda and y.dtype == torch.float32):
+        for layer in layers:
+            y = layer(y)
+        return y
+    bn, _, drop = layers
+    use_batch = bn.training or (bn.running_mean is None and bn.running_var is None)
+    if use_batch and y.shape[0] <= 1:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
+    momentum = bn.momentum
+    run_mean = run_var = None
+    if bn.track_running_stats and bn.running_mean is not None:
+        run_mean, run_var = bn.running_mean, bn.running_var
+        if bn.training:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:          # cumulative moving average
+                momentum = 1.0 / float(bn.num_batches_tracked)
+    if use_batch and not bn.training:     # eval without running stats: batch statistics, nothing to update
+        run_mean = run_var = None
+    if not use_batch and run_mean is None:
+        for layer in layers:
+            y = layer(y)
+        return y
+    p = float(drop.p) if drop.training else 0.0
+    seed = _draw_seed() if p > 0.0 else 0
+    # `training` selects batch statistics; dropout is gated by its own p
+    yc = _require_cuda_f32("y", y, 2)
+    upd_mean, upd_var = (run_mean, run_var) if (bn.training or not use_batch) else (None, None)
+    return _FeatureTailFunction.apply(yc, bn.weight, bn.bias, upd_mean, upd_var, use_batch, momentum or 0.0,
+                                      bn.eps, p, seed)
 
 
 # -------------------------------------------------------------------------- triu

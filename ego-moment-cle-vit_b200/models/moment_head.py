@@ -132,9 +132,7 @@ class MomentHead(nn.Module):
                                       eps=self.eps, third_order=self.use_third_order)
         if fused is not None:
             y, u = fused if self.use_third_order else (fused, None)
-            for layer in list(self.second_net)[1:]:
-                y = layer(y)
-            features = [y]
+            features = [EF.feature_tail(y, list(self.second_net)[1:])]
             if self.use_third_order:
                 features.append(self._feature_net(self.third_net, self.tensor_sketch(u)))
             return torch.cat(features, dim=-1)
@@ -159,12 +157,9 @@ class MomentHead(nn.Module):
     def _feature_net(net: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         """Linear -> BatchNorm1d -> GELU -> Dropout (moment_head.py:186-200). The parameters stay
         in the reference's nn.Sequential; the Linear's GEMMs (fwd, dx, dW) run on the library's
-        tcgen05 engine, BN/GELU/Dropout on torch."""
+        GEMM engines and BatchNorm + GELU + Dropout as one kernel each way (functional.feature_tail)."""
         lin = net[0]
-        x = EF.linear(x, lin.weight, lin.bias)
-        for layer in list(net)[1:]:
-            x = layer(x)
-        return x
+        return EF.feature_tail(EF.linear(x, lin.weight, lin.bias), list(net)[1:])
 
 
 def test_moment_head():

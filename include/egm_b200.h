@@ -74,7 +74,12 @@ int egm_prof_read(int i, float* ms, double* flops, int* dims);
  * a, p [B,N,D]; coef [(P+1)*(Q+1)] = softplus(alpha) on the device; G [B,N,N].
  * Saved for backward: Ra, Rp [B,N,ldR] with ldR = egm_gpf_ldr(N); nrm_a, nrm_p [B,N]; optionally
  * xn_state (egm_gpf_state_bytes; opaque: the normalised tokens as GEMM operands). xn_state == NULL
- * in both calls selects the memory-saving mode: the backward re-normalises the tokens instead. */
+ * in both calls selects the memory-saving mode: the backward re-normalises the tokens instead.
+ * egm_gpf_fused_ok(N, D, P, Q, prec) != 0: egm_gpf_fwd called with xn_state == NULL runs as ONE fused
+ * pass over the tokens (both Gram matrices on tcgen05 from fp32 tokens converted on the fly, cosine
+ * scaling + polynomial + clamp in the epilogue; gpf_kernel.py:117-159). Then Ra == Rp == NULL is
+ * allowed (forward-only call: nothing but G and the norms is written) and `ws` is unused. */
+int egm_gpf_fused_ok(int N, int D, int P, int Q, int prec);
 long long egm_gpf_ldr(int N);
 size_t egm_gpf_state_bytes(int B, int N, int D, int prec);
 size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec);
@@ -207,6 +212,22 @@ int egm_gram_bwd(const float* dR, const float* x, const float* nrm, int B, int N
 int egm_normalize_graph(const float* G, int B, int N, int method, float eps, float* out, float* deg,
                         egm_stream_t stream);
 int egm_batch_trace(const float* M, int B, int D, float* tr, egm_stream_t stream);
+
+/* ---- feature-net tail: BatchNorm1d -> GELU -> Dropout ---------------------------------------
+ * The layers that follow the Linear of second_net / third_net (moment_head.py:186-191, 195-200) in one
+ * launch each way. y [M,N] = the Linear's output. training != 0: batch statistics (biased variance),
+ * running_mean / running_var (optional) updated in place with `momentum` and the unbiased variance
+ * exactly like nn.BatchNorm1d, inverted dropout with keep-mask = hash(seed, element) >= drop_p (the
+ * same seed must be passed to the backward; the mask is NOT torch's Philox stream). training == 0:
+ * running statistics, no dropout. GELU is the exact erf form. save_mean / save_rstd [N] are outputs. */
+int egm_feature_tail_fwd(const float* y, int M, int N, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int training, float momentum, float bn_eps,
+                         float drop_p, unsigned long long seed, float* out, float* save_mean, float* save_rstd,
+                         egm_stream_t stream);
+int egm_feature_tail_bwd(const float* dout, const float* y, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_rstd, int M, int N, int training,
+                         float drop_p, unsigned long long seed, float* dy, float* dgamma, float* dbeta,
+                         egm_stream_t stream);
 
 /* Plain batched product C = alpha * op(A) op(B) through the active engine (used by the
  * native tests and the benchmark's tensor-pipe probe). A [B, M|K, K|M], B [B, K|N, N|K]. */

@@ -162,12 +162,13 @@ def test_fused_head_is_shard_invariant_at_B256(pkg, dev):
 
 # -------------------------------------------------- structured inputs through train-mode BatchNorm
 @pytest.mark.parametrize("name,maker,gate", [("cfg1_structured_trainbn", make_structured_inputs, 1e-3),
-                                             ("cfg1_trainbn", make_inputs, 5e-3)])
+                                             ("cfg1_trainbn", make_inputs, 1e-3)])
 def test_train_mode_batchnorm_parity(pkg, dev, name, maker, gate):
     """Config-1 shape, train-mode BatchNorm1d after the head's Linear, against the reference's fp32 run.
     Structured tokens (per-image scale / mean / low-rank covariance) hold the north star's
     1e-3 after BatchNorm; iid tokens have degenerate batch statistics (pre-BN batch std ~2e-5, which BN
-    amplifies ~50x) - that case is measured and recorded, gated at 5e-3."""
+    amplifies ~50x) - measured 3.5e-4 there (profiles/r02_parity_report.jsonl), so that
+    case is held to 1e-3 as well (round 1 gated it at 5e-3 without recording a value)."""
     rec = golden(name)
     B, N, D, P, Q, K, d_out = [int(v) for v in rec["cfg"][:7]]
     torch.manual_seed(0)
@@ -245,3 +246,106 @@ def test_early_grad_hook_sees_dW_before_the_chain_and_changes_nothing(pkg, dev):
     assert l0 < at < l1 and (l1 - at) >= 6      # the Newton-Schulz backward is enqueued after the hand-over
     for x, y in zip(base, got):
         assert torch.equal(x, y)
+
+
+# ------------------------------------------- BatchNorm1d + GELU + Dropout as one kernel
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("M,N", [(256, 256), (6, 8), (37, 70)])
+def test_feature_tail_matches_torch_layers(pkg, dev, train, M, N):
+    """functional.feature_tail vs the nn.BatchNorm1d -> nn.GELU -> nn.Dropout(p=0) modules themselves
+    (moment_head.py:186-191): outputs, input / gamma / beta gradients, and the in-place running-stat update."""
+    EF = pkg.functional
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    y = (torch.randn(M, N, generator=g) * 0.7 + torch.randn(1, N, generator=g)).to(dev)
+    dout = torch.randn(M, N, generator=g).to(dev)
+
+    def make():
+        torch.manual_seed(3)
+        layers = [torch.nn.BatchNorm1d(N), torch.nn.GELU(), torch.nn.Dropout(0.0)]
+        with torch.no_grad():
+            layers[0].weight.uniform_(0.5, 1.5)
+            layers[0].bias.uniform_(-0.3, 0.3)
+            layers[0].running_mean.uniform_(-0.2, 0.2)
+            layers[0].running_var.uniform_(0.5, 2.0)
+        net = torch.nn.Sequential(*layers).to(dev)
+        return net.train(train)
+
+    ref, mine = make(), make()
+    y1 = y.clone().requires_grad_(True)
+    o1 = ref(y1)
+    (o1 * dout).sum().backward()
+    y2 = y.clone().requires_grad_(True)
+    o2 = EF.feature_tail(y2, list(mine))
+    (o2 * dout).sum().backward()
+    assert rel_err(npy(o2), npy(o1)) < 2e-6
+    assert rel_err(npy(y2.grad), npy(y1.grad)) < 2e-5
+    assert rel_err(npy(mine[0].weight.grad), npy(ref[0].weight.grad)) < 2e-5
+    assert rel_err(npy(mine[0].bias.grad), npy(ref[0].bias.grad)) < 2e-5
+    assert rel_err(npy(mine[0].running_mean), npy(ref[0].running_mean)) < 1e-6
+    assert rel_err(npy(mine[0].running_var), npy(ref[0].running_var)) < 1e-6
+    assert int(mine[0].num_batches_tracked) == int(ref[0].num_batches_tracked)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+
+
+def test_feature_tail_dropout_contract(pkg, dev):
+    """Inverted dropout inside the fused kernel: keep-rate ~ 1-p, kept entries scaled by 1/(1-p), the
+    backward uses the same mask, reproducible under torch.manual_seed, off in eval mode."""
+    EF = pkg.functional
+    M, N, p = 512, 256, 0.1
+    layers = [torch.nn.BatchNorm1d(N).to(dev), torch.nn.GELU(), torch.nn.Dropout(p)]
+    for l in layers:
+        l.train()
+    y = torch.randn(M, N, device=dev) + 2.0
+    nodrop = EF.feature_tail(y, [layers[0], layers[1], torch.nn.Dropout(0.0).train()])
+    torch.manual_seed(11)
+    yy = y.clone().requires_grad_(True)
+    out = EF.feature_tail(yy, layers)
+    kept = out != 0
+    rate = float(kept.float().mean())
+    live = float((nodrop != 0).float().mean())
+    assert abs(rate - live * (1 - p)) < 0.01
+    assert torch.allclose(out[kept], nodrop[kept] / (1 - p), rtol=1e-6, atol=1e-7)
+    out.sum().backward()
+    assert bool((yy.grad[:, 0].abs().sum() > 0))
+    torch.manual_seed(11)
+    out2 = EF.feature_tail(y, layers)
+    assert torch.equal(out2, out.detach())                     # same seed -> same mask
+    out3 = EF.feature_tail(y, layers)
+    assert not torch.equal(out3, out.detach())                 # the generator advanced
+    for l in layers:
+        l.eval()
+    ev = EF.feature_tail(y, layers)
+    assert float((ev == 0).float().mean()) < 0.01              # no dropout in eval mode
+    with pytest.raises(ValueError, match="more than 1 value"):
+        for l in layers:
+            l.train()
+        EF.feature_tail(y[:1], layers)
+
+
+def test_feature_tail_other_layer_stacks_are_applied_as_they_are(pkg, dev):
+    EF = pkg.functional
+    y = torch.randn(5, 7, device=dev)
+    layers = [torch.nn.LayerNorm(7).to(dev), torch.nn.ReLU()]
+    assert torch.equal(EF.feature_tail(y, layers), layers[1](layers[0](y)))
+
+
+def test_strict_fp32_linear_runs_on_the_library(pkg, dev):
+    """fp32_simt mode: F.linear forward / dx / dW on the library's FFMA engine (no torch GEMM)."""
+    EF = pkg.functional
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(7, 100, generator=g).to(dev).requires_grad_(True)
+    w = torch.randn(5, 100, generator=g).to(dev).requires_grad_(True)
+    b = torch.randn(5, generator=g).to(dev).requires_grad_(True)
+    dy = torch.randn(7, 5, generator=g).to(dev)
+    l0 = lib.egm_launch_count()
+    y = EF.linear(x, w, b, precision="fp32_simt")
+    (y * dy).sum().backward()
+    assert lib.egm_launch_count() - l0 >= 3
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    y2 = torch.nn.functional.linear(x2, w2, b2)
+    (y2 * dy).sum().backward()
+    assert rel_err(npy(y), npy(y2)) < 1e-6
+    assert rel_err(npy(x.grad), npy(x2.grad)) < 1e-6
+    assert rel_err(npy(w.grad), npy(w2.grad)) < 1e-6
+    assert rel_err(npy(b.grad), npy(b2.grad)) < 1e-6
