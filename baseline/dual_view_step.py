@@ -80,7 +80,7 @@ def run(args, B):
     EF = pkg.functional
     egm_dist = importlib.import_module("ego-moment-cle-vit_b200.dist")
     lib = pkg._lib.load()
-    world, rank, local, dev = B.dist_setup()
+    world, rank, local, dev = B.dist_setup(not args.nccl_normal_priority)
     if RL.find_reference_root() is None:
         if rank == 0:
             print(json.dumps({"metric": "EGO-Moment-CLE-ViT dual-view training step images/sec",

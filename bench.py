@@ -75,6 +75,8 @@ def parse():
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic: skip the gradient all-reduce (N>1)")
     ap.add_argument("--no-overlap", action="store_true", help="diagnostic: all-reduce after backward, no hooks")
     ap.add_argument("--bucket-mb", type=int, default=32, help="gradient bucket / chunk size in MB")
+    ap.add_argument("--nccl-normal-priority", action="store_true",
+                    help="diagnostic: NCCL on a normal-priority stream (default: high priority)")
     ap.add_argument("--backbone-amp", action="store_true",
                     help="--config 4 only: run the ViT backbone under bf16 autocast (the reference ships amp: false)")
     ap.add_argument("--gemm-breakdown", action="store_true",
@@ -376,7 +378,7 @@ def read_prof(lib):
     return recs
 
 
-def dist_setup():
+def dist_setup(high_priority=True):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -387,7 +389,15 @@ def dist_setup():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL's kernels on a high-priority stream: when SMs free up at a kernel boundary the all-reduce's
+        # CTAs are placed first instead of queueing behind the persistent GEMM CTAs of the next launch
+        opts = None
+        if high_priority:
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:
+                opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     return world, rank, local, dev
 
 
@@ -442,7 +452,7 @@ def run_native(args):
     egm_dist = importlib.import_module("ego-moment-cle-vit_b200.dist")
     lib = pkg._lib.load()
 
-    world, rank, local, dev = dist_setup()
+    world, rank, local, dev = dist_setup(not args.nccl_normal_priority)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
@@ -737,7 +747,8 @@ def run_native(args):
             "l2": "two rotating input sets per GPU (310 MB each at the configs[1] shape, > 126 MB L2); no explicit flush",
             "order": "warm-up, e2e region, device-resident region, side modes",
             "allreduce": ("off (diagnostic)" if args.no_allreduce else
-                          f"{args.bucket_mb} MB chunks, NCCL AVG, " +
+                          f"{args.bucket_mb} MB chunks, NCCL AVG on a " +
+                          ("normal" if args.nccl_normal_priority else "high") + "-priority stream, " +
                           ("after backward" if args.no_overlap else
                            "dW of the Linear handed over before the Newton-Schulz backward"))}),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,

@@ -19,7 +19,7 @@ SOURCES = ["egm_api.cu", "egm_lowrank.cu", "egm_gemm_tc.cu", "egm_gemm_simt.cu",
            "egm_error.cu"]
 HEADERS = ["egm_gemm.h", "egm_chain.h", "egm_kernels.cuh", "egm_ptx.cuh", os.path.join("..", "..", "include", "egm_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-         "-shared", "-Xcompiler", "-fPIC"]
+         "-shared", "-Xcompiler", "-fPIC"] + os.environ.get("EGM_NVCC_FLAGS", "").split()   # e.g. -DEGM_GPF_PROFILE
 
 
 def _fingerprint() -> str:

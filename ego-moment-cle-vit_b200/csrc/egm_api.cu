@@ -1063,7 +1063,9 @@ int egm_feature_tail_bwd(const float* dout, const float* y, const float* gamma, 
 
 size_t egm_bmm_workspace(int B, int M, int N, int K, int prec) {
   (void)prec;
-  return pad256(w_bytes(B, M > K ? M : K, M > K ? M : K)) + pad256(w_bytes(B, N > K ? N : K, N > K ? N : K)) + 1024;
+  // either orientation of each operand (the row padding depends on which extent is the row length)
+  auto both = [&](int r, int c) { const size_t x = w_bytes(B, r, c), y = w_bytes(B, c, r); return x > y ? x : y; };
+  return pad256(both(M, K)) + pad256(both(K, N)) + 1024;
 }
 int egm_bmm(const float* A, int transA, const float* Bm, int transB, int B, int M, int N, int K,
             float alpha, float* C, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {

@@ -41,15 +41,19 @@ namespace {
 
 constexpr int kRowsMax = 208;                 // token rows per operand slot (N <= 208)
 constexpr int kPlane = kRowsMax * 128;        // one bf16 plane of a slot: rows x 64 bf16 (26 KiB)
-constexpr int kStgSlots = 3;                  // fp32 staging ring: boxes of 32 features
+// The staging ring is what keeps HBM busy: a slot is occupied from the TMA issue until the converters
+// release it (~2 us of memory latency + transfer, then ~0.3 us of conversion), so the bytes in flight
+// per SM are (slots - 1) x 26 KiB. Three slots measured 2.1 TB/s (latency-bound, ncu: the workers wait
+// on stg_full); five slots cover the per-SM share of HBM bandwidth at that latency.
+constexpr int kStgSlots = 5;                  // fp32 staging ring: boxes of 32 features
 constexpr int kStgBytes = kRowsMax * 128;     // rows x 32 fp32
-constexpr int kOpSlots = 2;                   // operand ring: 2 slots x 2 halves of 32 K-elements
+constexpr int kOpUnits = 2;                   // operand ring: the two 64-byte halves of one 128-byte-row slot
 constexpr int kOpBytes = 2 * kPlane;          // hi + lo
 constexpr int kWorkers = 8;                   // converter / epilogue warps
 constexpr int kThreadsF = 32 * (2 + kWorkers);
-constexpr int kTbuf = 32 * 33 * 4;            // per-warp transpose buffer
+constexpr int kTbuf = 32 * 17 * 4;            // per-warp transpose buffer (16 columns at a time)
 constexpr int kMaxCoef = 256;
-constexpr int kSmemF = 1024 + kStgSlots * kStgBytes + kOpSlots * kOpBytes + kWorkers * kTbuf +
+constexpr int kSmemF = 1024 + kStgSlots * kStgBytes + kOpBytes + kWorkers * kTbuf +
                        2 * kRowsMax * 4 + kMaxCoef * 4 + 256;
 
 struct FusedParams {
@@ -80,8 +84,8 @@ __device__ __forceinline__ void powers(float x, int deg, float (&pw)[MD + 1]) {
   }
 }
 // sum_{p,q} c[p][q] pa[p] pb[q]; c is zero-padded to (MD+1) x (MD+1)
-template <int MD>
-__device__ __forceinline__ float poly(const float (&pa)[MD + 1], const float (&pb)[MD + 1], const float* c) {
+template <int MD, typename C>
+__device__ __forceinline__ float poly(const float (&pa)[MD + 1], const float (&pb)[MD + 1], const C& c) {
   float f = 0.f;
 #pragma unroll
   for (int p = MD; p >= 0; --p) {
@@ -100,9 +104,9 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t stg = base;
   const uint32_t ops = stg + kStgSlots * kStgBytes;
-  const uint32_t tbuf0 = ops + kOpSlots * kOpBytes;
-  float* tbuf_gen = reinterpret_cast<float*>(gen + kStgSlots * kStgBytes + kOpSlots * kOpBytes);
-  float* inv_gen = tbuf_gen + kWorkers * 32 * 33;            // [2][kRowsMax] 1/max(norm, eps)
+  const uint32_t tbuf0 = ops + kOpBytes;
+  float* tbuf_gen = reinterpret_cast<float*>(gen + kStgSlots * kStgBytes + kOpBytes);
+  float* inv_gen = tbuf_gen + kWorkers * 32 * 17;            // [2][kRowsMax] 1/max(norm, eps)
   float* coef_gen = inv_gen + 2 * kRowsMax;                  // (MD+1)^2, zero padded (MD=15: 256)
   const uint32_t bars = tbuf0 + kWorkers * kTbuf + 2 * kRowsMax * 4 + kMaxCoef * 4;
   auto stg_full = [&](int s) { return bars + 8u * s; };
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
     ptx::prefetch_tensormap(&p.tm[0]);
     ptx::prefetch_tensormap(&p.tm[1]);
     for (int s = 0; s < kStgSlots; ++s) { ptx::mbar_init(stg_full(s), 1); ptx::mbar_init(stg_empty(s), kWorkers); }
-    for (int h = 0; h < 4; ++h) { ptx::mbar_init(op_full(h), kWorkers); ptx::mbar_init(op_empty(h), 1); }
+    for (int h = 0; h < kOpUnits; ++h) { ptx::mbar_init(op_full(h), kWorkers); ptx::mbar_init(op_empty(h), 1); }
     ptx::mbar_init(tfull, 1);
     ptx::mbar_init(tempty, kWorkers);
     ptx::fence_barrier_init();
@@ -154,11 +158,15 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
           const int s = n % kStgSlots;
           ptx::mbar_wait(stg_empty(s), ((n / kStgSlots) & 1u) ^ 1u);
           if (issuer) {
-            ptx::mbar_arrive_expect_tx(stg_full(s), 2u * box_rows * 128u);
+            // row tile 1 needs token rows 128..N-1 only: one box when they fit (rows past it feed
+            // accumulator lanes of tokens that do not exist)
+            const int row0 = r * 128;
+            const bool two = row0 + box_rows < N;
+            ptx::mbar_arrive_expect_tx(stg_full(s), (two ? 2u : 1u) * box_rows * 128u);
             const CUtensorMap* tm = &p.tm[u & 1];
-            const int k0 = (u >> 1) * 32, row0 = r * 128;
+            const int k0 = (u >> 1) * 32;
             ptx::tma_load_3d(tm, stg_full(s), stg + s * kStgBytes, k0, row0, b);
-            ptx::tma_load_3d(tm, stg_full(s), stg + s * kStgBytes + box_rows * 128, k0, row0 + box_rows, b);
+            if (two) ptx::tma_load_3d(tm, stg_full(s), stg + s * kStgBytes + box_rows * 128, k0, row0 + box_rows, b);
           }
           __syncwarp();
         }
@@ -173,11 +181,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
         ptx::mbar_wait(tempty, (tiles & 1u) ^ 1u);          // the previous tile's epilogue has drained TMEM
         ptx::tc_fence_after();
         for (int u = 0; u < units; ++u, ++n) {
-          const int hs = n & 3;
-          ptx::mbar_wait(op_full(hs), (n >> 2) & 1u);
+          const int hs = n & 1;
+          ptx::mbar_wait(op_full(hs), (n >> 1) & 1u);
           ptx::tc_fence_after();
           if (issuer) {
-            const uint32_t hi = ops + (hs >> 1) * kOpBytes + (hs & 1) * 64;
+            const uint32_t hi = ops + hs * 64;
             const uint32_t d = tmem + (u & 1) * 256;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
@@ -200,45 +208,60 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
       }
   } else {
     // ------------------------------------------------- converters, then the tile's epilogue
+    // 8 worker warps, one slot row per thread. (16 workers with half a row each measured SLOWER, 220 vs
+    // 166 us: 18 warps cap the kernel at 96 registers and every extra warp adds its own barrier round
+    // trip per unit; the unit's latency chain - wait, load, convert, store, proxy fence, arrive, MMA -
+    // not the issue rate, is what bounds this kernel.)
     const int w = warp - 2;
-    const int t = w * 32 + lane;                 // the slot row this thread converts
+    const int t = w * 32 + lane;                              // slot row
+#ifdef EGM_GPF_PROFILE
+    long long pf_wait_stg = 0, pf_wait_op = 0, pf_conv = 0, pf_wait_t = 0, pf_epi = 0, pf_bar = 0, pf_t0 = clock64();
+#define PF(acc) do { const long long c_ = clock64(); acc += c_ - pf_t0; pf_t0 = c_; } while (0)
+#else
+#define PF(acc) do {} while (0)
+#endif
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
-    const int half = w >> 2;                     // which half of the column chunks it takes
-    float* tb = tbuf_gen + w * 32 * 33;
+    const int cg = w >> 2;                       // its share of the 16-column chunks: c16 = cg, cg + 4, ...
+    float creg[MD <= 3 ? (MD + 1) * (MD + 1) : 1];
+    if (MD <= 3) {
+#pragma unroll
+      for (int k = 0; k < (MD + 1) * (MD + 1); ++k) creg[MD <= 3 ? k : 0] = coef_gen[k];
+    }
+    float* tb = tbuf_gen + w * 32 * 17;
     uint32_t n = 0, tiles = 0;
     for (int b = blockIdx.x; b < p.B; b += gridDim.x)
       for (int r = 0; r < ntile; ++r, ++tiles) {
         const int row_base = r * 128;            // global row of slot row 0
-        const int rows = r == 0 ? NP : 128;      // slot rows that feed an operand
-        const bool mine = t < rows && t < kRowsMax;
+        // slot rows that must hold real operands: every column of the tile (B operand) and every row
+        // whose token exists (A operand); the rest feeds accumulator lanes nobody reads
+        const int rows = r == 0 ? NP : NP - 128;
+        const bool mine = t < rows;
         float ssq[2] = {0.f, 0.f};
         for (int u = 0; u < units; ++u, ++n) {
-          const int s = n % kStgSlots, hs = n & 3;
+          const int s = n % kStgSlots, hs = n & 1;
           ptx::mbar_wait(stg_full(s), (n / kStgSlots) & 1u);
-          ptx::mbar_wait(op_empty(hs), ((n >> 2) & 1u) ^ 1u);
+          PF(pf_wait_stg);
+          ptx::mbar_wait(op_empty(hs), ((n >> 1) & 1u) ^ 1u);
+          PF(pf_wait_op);
           if (mine) {
             const uint32_t src = stg + s * kStgBytes + t * 128;
-            const uint32_t dst = ops + (hs >> 1) * kOpBytes + t * 128;
+            const uint32_t dst = ops + t * 128;
             const uint32_t sw = t & 7;
-            float acc = ssq[u & 1];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;    // independent partial sums of squares
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {        // 8 features -> one 16-byte bf16 chunk per plane
-              float v[8];
+            for (int hh = 0; hh < 2; ++hh) {     // 16 features at a time: loads in flight before the math
+              uint32_t x[16];
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                uint32_t x0, x1, x2, x3;
+              for (int c = 0; c < 4; ++c)
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                             : "r"(src + (((2 * c + h2) ^ sw) << 4)));
-                v[4 * h2] = __uint_as_float(x0); v[4 * h2 + 1] = __uint_as_float(x1);
-                v[4 * h2 + 2] = __uint_as_float(x2); v[4 * h2 + 3] = __uint_as_float(x3);
-              }
-              uint32_t hw[4], lw[4];
+                             : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                             : "r"(src + (((4 * hh + c) ^ sw) << 4)));
+              uint32_t hw[8], lw[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = v[2 * e], x1 = v[2 * e + 1];
-                acc = fmaf(x0, x0, acc);
-                acc = fmaf(x1, x1, acc);
+              for (int e = 0; e < 8; ++e) {
+                const float x0 = __uint_as_float(x[2 * e]), x1 = __uint_as_float(x[2 * e + 1]);
+                if (e & 1) { a2 = fmaf(x0, x0, a2); a3 = fmaf(x1, x1, a3); }
+                else { a0 = fmaf(x0, x0, a0); a1 = fmaf(x1, x1, a1); }
                 uint32_t h;
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
                 hw[e] = h;
@@ -246,11 +269,15 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
                     : "=r"(lw[e])
                     : "f"(x1 - __uint_as_float(h & 0xFFFF0000u)), "f"(x0 - __uint_as_float(h << 16)));
               }
-              const uint32_t off = (((hs & 1) * 4 + c) ^ sw) << 4;
-              ptx::sts128(dst + off, hw[0], hw[1], hw[2], hw[3]);
-              if (p.npass == 3) ptx::sts128(dst + kPlane + off, lw[0], lw[1], lw[2], lw[3]);
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {      // 8 features -> one 16-byte bf16 chunk per plane
+                const uint32_t off = ((hs * 4 + 2 * hh + c) ^ sw) << 4;
+                ptx::sts128(dst + off, hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+                if (p.npass == 3)
+                  ptx::sts128(dst + kPlane + off, lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+              }
             }
-            ssq[u & 1] = acc;
+            ssq[u & 1] += (a0 + a1) + (a2 + a3);
           }
           ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
           __syncwarp();
@@ -258,11 +285,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
             ptx::mbar_arrive(op_full(hs));
             ptx::mbar_arrive(stg_empty(s));
           }
+          PF(pf_conv);
         }
         // norms of this tile's rows -> shared (scaling of the columns) and global (saved for backward)
-        if (mine) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
+        for (int v = 0; v < 2; ++v) {
+          if (mine) {
             const float nr = sqrtf(ssq[v]);
             inv_gen[v * kRowsMax + t] = p.cosine ? 1.f / fmaxf(nr, p.eps) : 1.f;
             const int gr = row_base + t;
@@ -270,74 +298,110 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
+        PF(pf_bar);
         // ------------------------------------------------------------------- epilogue
         ptx::mbar_wait(tfull, tiles & 1u);
         ptx::tc_fence_after();
+        PF(pf_wait_t);
         const int li = q * 32 + lane;            // row within the tile = TMEM lane
         const int i = row_base + li;             // global row
         const int ncols = r == 0 ? NP : NP - 128;
-        const int nch = (ncols + 31) / 32;
-        const int c_lo = half * ((nch + 1) / 2), c_hi = half ? nch : (nch + 1) / 2;
-        const float ia_i = inv_gen[li], ip_i = inv_gen[kRowsMax + li];   // slot row li is global row i
+        const int nch = ncols / 16;              // NP is a multiple of 16
+        const int lic = min(li, kRowsMax - 1);
+        const float ia_i = inv_gen[lic], ip_i = inv_gen[kRowsMax + lic];   // slot row li is global row i
         const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const int row0 = row_base + q * 32;      // first global row of this warp
         float* Gb = p.G + (long long)b * N * N;
-        for (int c = c_lo; c < c_hi; ++c) {
-          const int lj0 = c * 32;                // column within the tile == slot row of that token
+        for (int c = cg; c < nch; c += kWorkers / 4) {
+          const int lj0 = c * 16;                // column within the tile == slot row of that token
           const int j0 = row_base + lj0;         // global column
-          if (j0 + 31 < row_base + q * 32) continue;      // chunk entirely below the diagonal (warp-uniform)
-          uint32_t va[32], vp[32];
-          ptx::tmem_ld_32x32(t_row + lj0, va);
-          ptx::tmem_ld_32x32(t_row + 256 + lj0, vp);
-          ptx::tmem_ld_wait();
-          float g[32];
+          if (j0 + 15 < row0 || row0 >= N) continue;      // chunk entirely below the diagonal / no rows (warp-uniform)
+          uint32_t va[16], vp[16];
+          ptx::tmem_ld_32x16(t_row + lj0, va);
+          ptx::tmem_ld_32x16(t_row + 256 + lj0, vp);
+          // the 16 column scales are the same for every lane: four 16-byte broadcast loads per view
+          float sa[16], sp[16];
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int ljc = min(lj0 + jj, kRowsMax - 1);
-            const float ra = __uint_as_float(va[jj]) * ia_i * inv_gen[ljc];
-            const float rp = __uint_as_float(vp[jj]) * ip_i * inv_gen[kRowsMax + ljc];
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 x = *reinterpret_cast<const float4*>(inv_gen + lj0 + 4 * k4);
+            const float4 y = *reinterpret_cast<const float4*>(inv_gen + kRowsMax + lj0 + 4 * k4);
+            sa[4 * k4] = x.x * ia_i; sa[4 * k4 + 1] = x.y * ia_i; sa[4 * k4 + 2] = x.z * ia_i; sa[4 * k4 + 3] = x.w * ia_i;
+            sp[4 * k4] = y.x * ip_i; sp[4 * k4 + 1] = y.y * ip_i; sp[4 * k4 + 2] = y.z * ip_i; sp[4 * k4 + 3] = y.w * ip_i;
+          }
+          ptx::tmem_ld_wait();
+          float g[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float ra = __uint_as_float(va[jj]) * sa[jj];
+            const float rp = __uint_as_float(vp[jj]) * sp[jj];
             va[jj] = __float_as_uint(ra);
             vp[jj] = __float_as_uint(rp);
             float pa[MD + 1], pb[MD + 1];
             powers<MD>(ra, p.P, pa);
             powers<MD>(rp, p.Q, pb);
-            g[jj] = fmaxf(poly<MD>(pa, pb, coef_gen), 0.f);
+            g[jj] = fmaxf(MD <= 3 ? poly<MD>(pa, pb, creg) : poly<MD>(pa, pb, coef_gen), 0.f);
           }
-          const int row0 = row_base + q * 32;    // first global row of this warp
+          // interior chunk: every element is strictly above the diagonal and inside the matrix
+          const bool interior = j0 >= row0 + 32 && j0 + 16 <= N && row0 + 32 <= N;
           // three outputs share the two store patterns: G always, R_a / R_p when the backward will run
+#pragma unroll
           for (int o = 0; o < 3; ++o) {
             float* dstb;
-            long long ld;
+            int ld;
             if (o == 0) { dstb = Gb; ld = N; }
             else {
               float* R = o == 1 ? p.Ra : p.Rp;
               if (!R) break;
-              dstb = R + (long long)b * N * p.ldR; ld = p.ldR;
+              dstb = R + (long long)b * N * p.ldR; ld = (int)p.ldR;
             }
+            float val[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) val[jj] = o == 0 ? g[jj] : __uint_as_float(o == 1 ? va[jj] : vp[jj]);
             // mirrored store (j, i), j > i: lanes are consecutive i - coalesced as is
+            float* col = dstb + (long long)j0 * ld + i;
+            if (interior) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const int j = j0 + jj;
-              const float val = o == 0 ? g[jj] : __uint_as_float(o == 1 ? va[jj] : vp[jj]);
-              if (j > i && j < N && i < N) dstb[(long long)j * ld + i] = val;
+              for (int jj = 0; jj < 16; ++jj) { *col = val[jj]; col += ld; }
+            } else if (i < N) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                if (j0 + jj > i && j0 + jj < N) *col = val[jj];
+                col += ld;
+              }
             }
-            // direct store (i, j), j >= i: through the warp's transpose buffer
+            // direct store (i, j), j >= i: through the warp's transpose buffer (two rows per pass:
+            // lanes 0-15 row rr, lanes 16-31 row rr + 1)
             __syncwarp();
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              tb[lane * 33 + jj] = o == 0 ? g[jj] : __uint_as_float(o == 1 ? va[jj] : vp[jj]);
+            for (int jj = 0; jj < 16; ++jj) tb[lane * 17 + jj] = val[jj];
             __syncwarp();
-            const int j = j0 + lane;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int i2 = row0 + rr;
-              if (i2 < N && j >= i2 && j < N) dstb[(long long)i2 * ld + j] = tb[rr * 33 + lane];
+            const int jc = lane & 15, rh = lane >> 4;
+            const int j = j0 + jc;
+            float* rowp = dstb + (long long)(row0 + rh) * ld + j;
+            const float* tbr = tb + rh * 17 + jc;
+            if (interior) {
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) { *rowp = tbr[rr * 17]; rowp += 2 * ld; }
+            } else if (j < N) {
+#pragma unroll
+              for (int rr = 0; rr < 32; rr += 2) {
+                const int i2 = row0 + rr + rh;
+                if (i2 < N && j >= i2) *rowp = tbr[rr * 17];
+                rowp += 2 * ld;
+              }
             }
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty);
+        PF(pf_epi);
       }
+#ifdef EGM_GPF_PROFILE
+    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 120))
+      printf("gpf_prof blk %d warp %d: wait_stg %lld wait_op %lld conv %lld bar %lld wait_tfull %lld epi %lld\n",
+             (int)blockIdx.x, warp, pf_wait_stg, pf_wait_op, pf_conv, pf_bar, pf_wait_t, pf_epi);
+#endif
   }
   ptx::tc_fence_before();
   __syncthreads();

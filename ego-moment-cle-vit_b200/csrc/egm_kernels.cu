@@ -560,6 +560,10 @@ gpf_poly3_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
   }
 }
 
+// RSYM: R_a and R_p are symmetric bit for bit (written by the fused forward, which evaluates each pair
+// once): the mirror element has the same polynomial value, derivatives and power tables, so one
+// evaluation per pair suffices and only dG is read at the mirrored position.
+template <bool RSYM>
 __global__ void __launch_bounds__(256, 3)
 gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
                      const float* __restrict__ Rp, int ldR, const float* __restrict__ coef, int P, int Q,
@@ -582,8 +586,10 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
   for (int k = 0; k < 4; ++k) {
     const int r = ty + 8 * k;
     const bool okm = (j0 + r < n) && (i0 + tx < n);     // mirror tile (tj, ti)
-    sa[r][tx] = okm ? ra_b[(j0 + r) * ldR + i0 + tx] : 0.f;
-    sp[r][tx] = okm ? rp_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    if (!RSYM) {
+      sa[r][tx] = okm ? ra_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+      sp[r][tx] = okm ? rp_b[(j0 + r) * ldR + i0 + tx] : 0.f;
+    }
     sg[r][tx] = okm ? dg_b[(j0 + r) * n + i0 + tx] : 0.f;
     const bool ok = (i0 + r < n) && (j0 + tx < n);
     xa[k] = ok ? ra_b[(i0 + r) * ldR + j0 + tx] : 0.f;
@@ -600,10 +606,31 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
     const int r = ty + 8 * k;
     ea_k[k] = ep_k[k] = 0.f;
     if (i0 + r >= n) continue;   // warp-uniform: a warp owns one row of the tile
-    float f, fa, fb, ft, fat, fbt, pa[4], pb[4], pat[4], pbt[4];
+    float f, fa, fb, pa[4], pb[4];
     poly.eval_grad(xa[k], xp[k], f, fa, fb, pa, pb);
-    poly.eval_grad(sa[tx][r], sp[tx][r], ft, fat, fbt, pat, pbt);
     const float g_ij = xg[k], g_ji = sg[tx][r];       // both zero outside the matrix
+    if (RSYM) {
+      float dF_ij, dF_ji;
+      if (symmetric) {
+        dF_ij = dF_ji = (f >= 0.f) ? 0.5f * (g_ij + g_ji) : 0.f;
+      } else {
+        dF_ij = (f >= 0.f) ? g_ij : 0.f;
+        dF_ji = (f >= 0.f) ? g_ji : 0.f;
+      }
+      const float dsum = dF_ij + dF_ji;
+      ea_k[k] = dsum * fa;
+      ep_k[k] = dsum * fb;
+      const float dc = dF_ij + (offdiag ? dF_ji : 0.f);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        const float u = dc * pa[pp];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) acc[pp * 4 + qq] = fmaf(u, pb[qq], acc[pp * 4 + qq]);
+      }
+      continue;
+    }
+    float ft, fat, fbt, pat[4], pbt[4];
+    poly.eval_grad(sa[tx][r], sp[tx][r], ft, fat, fbt, pat, pbt);
     float dF_ij, dF_ji;
     if (symmetric) {
       const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
@@ -1610,12 +1637,20 @@ void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long l
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
                   cudaStream_t st) {
   dim3 grid(poly_pairs(n), batch);
-  if (P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31) && Ea.ld % 4 == 0)
-    gpf_poly3_bwd_kernel<<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n, wptr(Ea, prec),
-                                               wptr(Ep, prec), partial);
-  else
+  // bit 1 of `symmetric`: R_a / R_p are exactly symmetric (the fused forward wrote them)
+  const bool rsym = (symmetric & 2) != 0;
+  symmetric &= 1;
+  if (P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31) && Ea.ld % 4 == 0) {
+    if (rsym)
+      gpf_poly3_bwd_kernel<true><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
+                                                       wptr(Ea, prec), wptr(Ep, prec), partial);
+    else
+      gpf_poly3_bwd_kernel<false><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
+                                                        wptr(Ea, prec), wptr(Ep, prec), partial);
+  } else {
     gpf_poly_bwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n,
                                                        wptr(Ea, prec), wptr(Ep, prec), partial);
+  }
   note_launch();
   const int nt = (P + 1) * (Q + 1);
   reduce_partials_kernel<<<nt, 256, 0, st>>>(partial, nblocks, nt, dcoef);

@@ -136,7 +136,8 @@ class _GPFFunction(Function):
                                      _p(xn), prec, ws.data_ptr(), ws.numel(), _stream(dev)), "egm_gpf_fwd")
         if need_grad:
             ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm, *([xn] if keep else []))
-        ctx.cfg = (int(cosine), float(eps), int(symmetric), prec)
+        # bit 1: R_a / R_p are symmetric bit for bit (fused forward) - the backward evaluates each pair once
+        ctx.cfg = (int(cosine), float(eps), int(symmetric) | (2 if fused else 0), prec)
         return G
 
     @staticmethod

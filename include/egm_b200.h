@@ -78,7 +78,9 @@ int egm_prof_read(int i, float* ms, double* flops, int* dims);
  * egm_gpf_fused_ok(N, D, P, Q, prec) != 0: egm_gpf_fwd called with xn_state == NULL runs as ONE fused
  * pass over the tokens (both Gram matrices on tcgen05 from fp32 tokens converted on the fly, cosine
  * scaling + polynomial + clamp in the epilogue; gpf_kernel.py:117-159). Then Ra == Rp == NULL is
- * allowed (forward-only call: nothing but G and the norms is written) and `ws` is unused. */
+ * allowed (forward-only call: nothing but G and the norms is written) and `ws` is unused. R_a / R_p
+ * written by the fused pass are symmetric bit for bit; pass `symmetric | 2` to egm_gpf_bwd to let the
+ * backward evaluate each (i,j)/(j,i) pair once. */
 int egm_gpf_fused_ok(int N, int D, int P, int Q, int prec);
 long long egm_gpf_ldr(int N);
 size_t egm_gpf_state_bytes(int B, int N, int D, int prec);
