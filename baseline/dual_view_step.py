@@ -96,7 +96,8 @@ def run(args, B):
     egm_dist.broadcast_parameters(model)
     params = [p for p in model.parameters() if p.requires_grad]
     buckets = None if args.no_allreduce else egm_dist.GradBuckets(params, bucket_bytes=args.bucket_mb << 20,
-                                                                  overlap=not args.no_overlap)
+                                                                  overlap=not args.no_overlap,
+                                                                  chunk_bytes=(args.chunk_mb << 20) or None)
     opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)

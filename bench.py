@@ -74,7 +74,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip side modes / comparators / cpu baseline")
     ap.add_argument("--no-allreduce", action="store_true", help="diagnostic: skip the gradient all-reduce (N>1)")
     ap.add_argument("--no-overlap", action="store_true", help="diagnostic: all-reduce after backward, no hooks")
-    ap.add_argument("--bucket-mb", type=int, default=32, help="gradient bucket / chunk size in MB")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="gradient bucket size in MB (grouping of small gradients)")
+    ap.add_argument("--chunk-mb", type=int, default=0,
+                    help="diagnostic: split every gradient all-reduce into pieces of this many MB (0 = one launch)")
     ap.add_argument("--nccl-normal-priority", action="store_true",
                     help="diagnostic: NCCL on a normal-priority stream (default: high priority)")
     ap.add_argument("--backbone-amp", action="store_true",
@@ -389,6 +391,9 @@ def dist_setup(high_priority=True):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # a 302 MB all-reduce needs few CTAs over NVLink/NVSwitch; every CTA it holds is an SM the
+        # persistent GEMM CTAs of the Newton-Schulz backward cannot use (8 GPUs: 17.06 -> 16.99 ms/step)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         # NCCL's kernels on a high-priority stream: when SMs free up at a kernel boundary the all-reduce's
         # CTAs are placed first instead of queueing behind the persistent GEMM CTAs of the next launch
         opts = None
@@ -471,7 +476,8 @@ def run_native(args):
     params = list(gpf.parameters()) + list(head.parameters())
     buckets = None
     if not args.no_allreduce:
-        buckets = egm_dist.GradBuckets(params, bucket_bytes=args.bucket_mb << 20, overlap=not args.no_overlap)
+        buckets = egm_dist.GradBuckets(params, bucket_bytes=args.bucket_mb << 20, overlap=not args.no_overlap,
+                                       chunk_bytes=(args.chunk_mb << 20) or None)
     opt = torch.optim.SGD(params, lr=1e-6)
 
     # two rotating input sets, each 2 x B x N x D x 4 B (310 MB at the configs[1] shape, > 126 MB of L2)
@@ -747,7 +753,8 @@ def run_native(args):
             "l2": "two rotating input sets per GPU (310 MB each at the configs[1] shape, > 126 MB L2); no explicit flush",
             "order": "warm-up, e2e region, device-resident region, side modes",
             "allreduce": ("off (diagnostic)" if args.no_allreduce else
-                          f"{args.bucket_mb} MB chunks, NCCL AVG on a " +
+                          (f"{args.chunk_mb} MB chunks" if args.chunk_mb else "one launch per gradient bucket") +
+                          f", NCCL AVG (NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}) on a " +
                           ("normal" if args.nccl_normal_priority else "high") + "-priority stream, " +
                           ("after backward" if args.no_overlap else
                            "dW of the Linear handed over before the Newton-Schulz backward"))}),

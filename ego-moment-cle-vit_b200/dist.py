@@ -49,10 +49,13 @@ class GradBuckets:
     """DDP-style gradient averaging, overlapped with the backward of the path.
 
     * Parameters are grouped (reverse registration order = the order backward produces them) into
-      flat buckets of at most `bucket_bytes`; a bucket is averaged by asynchronous all-reduces of
-      `bucket_bytes`-sized chunks (NCCL `ReduceOp.AVG`; backends without AVG - gloo - sum and scale).
-      A single contiguous gradient is reduced in place (no staging copy for the 302 MB
-      `second_net.0.weight.grad`).
+      flat buckets of at most `bucket_bytes`; a bucket is averaged by ONE asynchronous all-reduce
+      (NCCL `ReduceOp.AVG`; backends without AVG - gloo - sum and scale), or by `chunk_bytes`-sized
+      pieces when that is set. A single contiguous gradient is reduced in place (no staging copy for
+      the 302 MB `second_net.0.weight.grad`). One launch is the default on purpose: the persistent GEMM
+      CTAs of the Newton-Schulz backward hold every SM, so a collective's CTAs are placed only at a
+      kernel boundary - ten 32 MB launches each wait for their own boundary and measured 0.35 ms
+      slower per step at 8 GPUs than one 302 MB launch (profiles/r02_n8_allreduce_variants.md).
     * `overlap=True` (default): a post-accumulate-grad hook launches a bucket the moment its last
       gradient exists. The fused `MomentHead` operator computes the weight gradient of its Linear
       FIRST and the whole Newton-Schulz backward after it inside one autograd node, so an ordinary
@@ -67,10 +70,11 @@ class GradBuckets:
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None,
-                 overlap: bool = True):
+                 overlap: bool = True, chunk_bytes: Optional[int] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.bucket_bytes = int(bucket_bytes)
+        self.chunk_bytes = int(chunk_bytes) if chunk_bytes else None
         self.overlap = bool(overlap)
         self.buckets: List[List[torch.nn.Parameter]] = []
         cur: List[torch.nn.Parameter] = []
@@ -107,7 +111,7 @@ class GradBuckets:
         world = dist.get_world_size(self.group)
         avg = self._has_avg()
         op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
-        step = max(1, self.bucket_bytes // flat.element_size())
+        step = max(1, self.chunk_bytes // flat.element_size()) if self.chunk_bytes else max(1, flat.numel())
         works = [dist.all_reduce(flat[o:o + step], op=op, group=self.group, async_op=True)
                  for o in range(0, flat.numel(), step)]
         return _Pending(works, flat, grads, inplace, 1.0 if avg else 1.0 / world)

@@ -446,7 +446,21 @@ def mark_symmetric(graph: torch.Tensor) -> torch.Tensor:
 
 
 def graph_is_symmetric(graph: torch.Tensor) -> bool:
-    return _symmetric_fast_path and getattr(graph, "_egm_symmetric_version", None) == graph._version
+    """True when MomentHead may take the symmetric fast path for `graph`: the tag written by
+    GraphPolynomialFusion matches the tensor's version counter (an in-place edit drops it), and nobody
+    observes the graph's own gradient - `graph.retain_grad()` or a tensor hook would see (dG + dG^T)/2
+    instead of the reference's dG, so those graphs take the general path. Writes that bypass the
+    version counter (`G.data.copy_()`, `set_()`) are not detected; under EGM_POISON=1 (the test
+    suite's debug mode) the tag is verified on the device before it is trusted."""
+    if not _symmetric_fast_path or getattr(graph, "_egm_symmetric_version", None) != graph._version:
+        return False
+    if graph.requires_grad and (graph.retains_grad or getattr(graph, "_backward_hooks", None)):
+        return False
+    if _poison and not torch.equal(graph, graph.transpose(-2, -1)):
+        raise RuntimeError("graph is tagged exactly symmetric but is not: it was edited without bumping its "
+                           "version counter (e.g. through .data); the symmetric fast path would read only its "
+                           "upper blocks")
+    return True
 
 
 _ns_algorithm = os.environ.get("EGM_NS_ALGORITHM", "dense")

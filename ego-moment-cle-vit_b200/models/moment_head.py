@@ -77,7 +77,17 @@ class TensorSketch(nn.Module):
 class MomentHead(nn.Module):
     """Graph-weighted 2nd (+ optional 3rd) order moment pooling head (moment_head.py:136-322).
 
-    forward(tokens [B,N,D], graph [B,N,N]) -> [B,d_out]. `graph` may be any real matrix."""
+    forward(tokens [B,N,D], graph [B,N,N]) -> [B,d_out]. `graph` may be any real matrix.
+
+    Gradient contract. Outputs, token gradients and parameter gradients are the reference's in every
+    case. When `graph` is the (exactly symmetric, tagged) output of GraphPolynomialFusion with
+    symmetric_enforce=True the head takes the symmetric fast path (upper tiles only, tangent-form
+    backward) and the gradient returned FOR THE GRAPH is the symmetric part (dG + dG^T)/2 of the
+    reference's dG - the gradient with respect to a symmetric matrix, and exactly what the
+    symmetrisation in GraphPolynomialFusion's backward lets through. A graph that is untagged,
+    edited in place, produced with symmetric_enforce=False, or observed (`graph.retain_grad()`, a
+    tensor hook) takes the general path and receives the reference's dG itself;
+    `functional.set_symmetric_fast_path(False)` turns the fast path off globally."""
 
     def __init__(self, d_in: int, d_out: int = 512, use_third_order: bool = False,
                  isqrt_iterations: int = 3, sketch_dim: int = 2048, eps: float = 1e-5):

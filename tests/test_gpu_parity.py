@@ -324,9 +324,11 @@ def test_small_goldens_forward_and_backward(pkg, dev, name, mode, fast):
         with EF.precision(mode):
             G = gpf(a, p)
             tagged = EF.graph_is_symmetric(G)
-            G.retain_grad()
             out = head(a, G)
-            (out * torch.from_numpy(rec["dOut"]).float().to(dev)).sum().backward()
+            # torch.autograd.grad captures the gradient that flows into G without observing the tensor
+            # (no hook, no retain_grad), so a tagged graph stays on the symmetric fast path
+            dG, da, dp, dal = torch.autograd.grad((out * torch.from_numpy(rec["dOut"]).float().to(dev)).sum(),
+                                                  [G, a, p, gpf.alpha_coeffs])
     finally:
         EF.set_symmetric_fast_path(True)
     assert tagged == (fast and bool(gpf.symmetric_enforce))
@@ -335,17 +337,42 @@ def test_small_goldens_forward_and_backward(pkg, dev, name, mode, fast):
         tol *= 20   # B=4 train-mode BatchNorm amplifies
     assert rel_err(npy(G), rec["G"]) < tol
     assert rel_err(npy(out), rec["out"]) < tol
-    assert rel_err(npy(gpf.alpha_coeffs.grad), rec["d_alpha"]) < 5 * tol
-    assert rel_err(npy(a.grad), rec["d_anchor"]) < 5 * tol
-    assert rel_err(npy(p.grad), rec["d_positive"]) < 5 * tol
+    assert rel_err(npy(dal), rec["d_alpha"]) < 5 * tol
+    assert rel_err(npy(da), rec["d_anchor"]) < 5 * tol
+    assert rel_err(npy(dp), rec["d_positive"]) < 5 * tol
     # the fused tensor-core head on a graph tagged symmetric returns the symmetric part of the
     # reference's graph gradient (include/egm_b200.h, EGM_MHD_SYMMETRIC_GRAPH); every other
     # combination returns the reference's gradient itself
     d_G = rec["d_G"]
     if tagged and mode == "fp32" and head.isqrt_cov.num_iterations >= 2:
         d_G = 0.5 * (d_G + np.swapaxes(d_G, -1, -2))
-        assert rel_err(npy(G.grad), npy(G.grad.transpose(-2, -1))) < 1e-4   # dW = V Zc^T rounds per element
-    assert rel_err(npy(G.grad), d_G) < 5 * tol
+        assert rel_err(npy(dG), npy(dG.transpose(-2, -1))) < 1e-4   # dW = V Zc^T rounds per element
+    assert rel_err(npy(dG), d_G) < 5 * tol
+
+
+@pytest.mark.parametrize("name", ["small_p2q2", "small_trainbn"])
+def test_observed_graph_gets_the_reference_gradient(pkg, dev, name):
+    """`G.retain_grad()` (or a tensor hook) on the tagged graph means somebody looks at dG
+    itself - such a graph leaves the symmetric fast path and G.grad is the reference's dG, not its
+    symmetric part, with the fast path switched on."""
+    rec = golden(name)
+    gpf, head = _build_from_golden(pkg, rec, dev)
+    EF = pkg.functional
+    a = torch.from_numpy(rec["anchor"]).float().to(dev).requires_grad_(True)
+    p = torch.from_numpy(rec["positive"]).float().to(dev).requires_grad_(True)
+    with EF.precision("fp32"):
+        G = gpf(a, p)
+        assert EF.graph_is_symmetric(G)
+        G.retain_grad()
+        assert not EF.graph_is_symmetric(G)
+        out = head(a, G)
+        (out * torch.from_numpy(rec["dOut"]).float().to(dev)).sum().backward()
+    tol = 5e-3 * (20 if name == "small_trainbn" else 1)
+    assert rel_err(npy(G.grad), rec["d_G"]) < tol
+    assert rel_err(npy(a.grad), rec["d_anchor"]) < tol
+    G2 = gpf(a, p)
+    G2.register_hook(lambda g: g)
+    assert not EF.graph_is_symmetric(G2)
 
 
 @pytest.mark.parametrize("mode", MODES)
