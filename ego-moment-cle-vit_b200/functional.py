@@ -700,11 +700,11 @@ def feature_tail(y, layers):
     layers = list(layers)
     nn = torch.nn
     if not (len(layers) == 3 and isinstance(layers[0], nn.BatchNorm1d) and isinstance(layers[1], nn.GELU)
-            and getattr(layers[1], "approximate", "none") == "none" and isinstance(layers[2], nn.Dropout)
-            and y.dim() == 2 and y.is_cuda and y.dtype == torch.float32):
-        for layer in layers:
+            and getattr(layers[1], "approximate", "none") == "none" and isinstance(layers[2], nn.Dropout)):
+        for layer in layers:          # a user-modified Sequential: not this library's business
             y = layer(y)
         return y
+    y = _require_cuda_f32("y", y, 2)   # the reference's own stack: CUDA only, like the rest of the path
     bn, _, drop = layers
     use_batch = bn.training or (bn.running_mean is None and bn.running_var is None)
     if use_batch and y.shape[0] <= 1:
@@ -726,9 +726,8 @@ def feature_tail(y, layers):
     p = float(drop.p) if drop.training else 0.0
     seed = _draw_seed() if p > 0.0 else 0
     # `training` selects batch statistics; dropout is gated by its own p
-    yc = _require_cuda_f32("y", y, 2)
     upd_mean, upd_var = (run_mean, run_var) if (bn.training or not use_batch) else (None, None)
-    return _FeatureTailFunction.apply(yc, bn.weight, bn.bias, upd_mean, upd_var, use_batch, momentum or 0.0,
+    return _FeatureTailFunction.apply(y, bn.weight, bn.bias, upd_mean, upd_var, use_batch, momentum or 0.0,
                                       bn.eps, p, seed)
 
 

@@ -423,3 +423,20 @@ def test_plain_c_host_links_and_calls_the_abi(pkg, tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=lib_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.startswith("abi ok"), (r.returncode, r.stdout, r.stderr)
+
+
+def test_feature_tail_has_no_cpu_path_for_the_reference_stack(pkg):
+    """BatchNorm1d -> GELU -> Dropout of second_net / third_net runs in the library: CPU tensors raise;
+    a Sequential tail that is not the reference's is applied layer by layer (not this library's business)."""
+    EF = pkg.functional
+    layers = [torch.nn.BatchNorm1d(4), torch.nn.GELU(), torch.nn.Dropout(0.1)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        EF.feature_tail(torch.randn(3, 4), layers)
+    other = [torch.nn.LayerNorm(4), torch.nn.ReLU()]
+    y = torch.randn(3, 4)
+    assert torch.equal(EF.feature_tail(y, other), other[1](other[0](y)))
+    # the data-parallel hand-over hook is a plain module-level slot
+    assert EF.get_early_grad_hook() is None
+    EF.set_early_grad_hook(print)
+    assert EF.get_early_grad_hook() is print
+    EF.set_early_grad_hook(None)
