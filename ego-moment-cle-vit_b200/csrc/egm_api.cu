@@ -7,6 +7,7 @@
 // and 6K-6 backward for K >= 2 instead of the reference's 4K / 8K (moment_head.py:53-64).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "egm_chain.h"
 
@@ -380,7 +381,8 @@ int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N,
 size_t egm_gpf_bwd_workspace(int B, int N, int D, int P, int Q, int prec) {
   (void)prec;
   return pad256(w_bytes(B, N, D)) + 2 * pad256(w_bytes(B, N, N)) + pad256((size_t)B * N * D * 4) +
-         pad256((size_t)k::gpf_poly_bwd_blocks(B, N) * (P + 1) * (Q + 1) * 4) + 1024;
+         pad256((size_t)k::gpf_poly_bwd_blocks(B, N) * (P + 1) * (Q + 1) * 4) +
+         pad256(k::gpf_poly_bwd_rowpart_floats(B, N) * 4) + pad256((size_t)B * N * 4) + 1024;
 }
 
 int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* coef, const float* Ra,
@@ -400,11 +402,19 @@ int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* co
   float* dxn = static_cast<float*>(ar.take((size_t)B * N * D * 4));
   const int nblocks = k::gpf_poly_bwd_blocks(B, N);
   float* partial = static_cast<float*>(ar.take((size_t)nblocks * (P + 1) * (Q + 1) * 4));
-  EGM_REQUIRE(wx && wea && wep && dxn && partial, EGM_ERR_WORKSPACE, "egm_gpf_bwd: workspace %zu < %zu",
-              ws_bytes, egm_gpf_bwd_workspace(B, N, D, P, Q, prec));
+  float* rowpart = static_cast<float*>(ar.take(k::gpf_poly_bwd_rowpart_floats(B, N) * 4));
+  float* nrm_scratch = static_cast<float*>(ar.take((size_t)B * N * 4));
+  EGM_REQUIRE(wx && wea && wep && dxn && partial && rowpart && nrm_scratch, EGM_ERR_WORKSPACE,
+              "egm_gpf_bwd: workspace %zu < %zu", ws_bytes, egm_gpf_bwd_workspace(B, N, D, P, Q, prec));
   const long long ldR = egm_gpf_ldr(N);
   const W Ea = make_w(wea, B, N, N), Ep = make_w(wep, B, N, N), Xn = make_w(wx, B, N, D);
-  k::gpf_poly_bwd(dG, Ra, Rp, ldR, coef, P, Q, symmetric, B, N, Ea, Ep, partial, nblocks, dcoef, prec, st);
+  // Without kept operand planes (always after the fused forward) and with cosine similarity, the
+  // backward of F.normalize is folded into E (k::gpf_poly_bwd): the product with the RAW token planes
+  // is the token gradient itself - no [B,N,D] rownorm_bwd pass, no fp32 round trip of d x-hat.
+  static const bool fold_off = []() { const char* e = getenv("EGM_GPF_FOLD"); return e && e[0] == '0'; }();
+  const bool fold = cosine && !xn_state && !fold_off && k::gpf_poly_bwd_can_fold(P, Q, N, ldR, Ea);
+  k::gpf_poly_bwd(dG, Ra, Rp, ldR, coef, P, Q, symmetric, B, N, Ea, Ep, partial, nblocks, dcoef, prec, st, nrm_a,
+                  nrm_p, eps, fold ? rowpart : nullptr);
   EGM_LAUNCHED();
   Arena xs(const_cast<void*>(xn_state), xn_state ? egm_gpf_state_bytes(B, N, D, prec) : 0);
   const W An = make_w(xs.take(w_bytes(B, N, D)), B, N, D), Pn = make_w(xs.take(w_bytes(B, N, D)), B, N, D);
@@ -413,17 +423,18 @@ int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* co
     const float* nrm = v ? nrm_p : nrm_a;
     float* dx = v ? dp : da;
     if (!xn_state) {
-      // memory-saving mode: re-materialise the normalised tokens instead of keeping 2 x [B,N,D] alive
-      k::rownorm(x, B, N, D, eps, cosine, dxn /*norms scratch, overwritten below*/, Xn, prec, st);
+      // re-materialise the token operand planes: raw tokens when the normalisation is folded into E,
+      // else the normalised ones (memory-saving mode of the staged path)
+      k::rownorm(x, B, N, D, eps, fold ? 0 : cosine, nrm_scratch, Xn, prec, st);
       EGM_LAUNCHED();
     }
     const W& Xv = xn_state ? (v ? Pn : An) : Xn;
-    GemmProblem g;  // d An = (dR + dR^T) An
+    GemmProblem g;  // d An = (dR + dR^T) An, or dx = E'' X
     g.M = N; g.N = D; g.batch = B; g.nterms = 1;
     g.t[0] = term(v ? Ep : Ea, 0, Xv, 0, N, prec);
-    g.Cf = f32_mat(cosine ? dxn : dx, N, D, D, (long long)N * D);
+    g.Cf = f32_mat((cosine && !fold) ? dxn : dx, N, D, D, (long long)N * D);
     EGM_CUDA(run_gemm(g, prec, st));
-    if (cosine) {
+    if (cosine && !fold) {
       k::rownorm_bwd(x, nrm, dxn, B, N, D, eps, dx, st);
       EGM_LAUNCHED();
     }

@@ -563,11 +563,21 @@ gpf_poly3_fwd_kernel(const float* __restrict__ Ra, const float* __restrict__ Rp,
 // RSYM: R_a and R_p are symmetric bit for bit (written by the fused forward, which evaluates each pair
 // once): the mirror element has the same polynomial value, derivatives and power tables, so one
 // evaluation per pair suffices and only dG is read at the mirrored position.
-template <bool RSYM>
+//
+// FOLD (cosine similarity): the backward of F.normalize is folded into E, so that the product with the
+// RAW token planes is the token gradient itself and no rownorm_bwd pass over [B,N,D] is needed:
+//   dx_i = (dxh_i - xh_i <xh_i, dxh_i>) / n_i,  dxh = E xh,  <xh_i, dxh_i> = sum_j E_ij R_ij =: s_i
+//   =>  dx = E'' X  with  E''_ij = (E_ij - [n_i >= eps] s_i delta_ij) / (m_i m_j),  m = max(n, eps)
+// (a row below the clamp has xh_i = x_i / eps and no projection term, gpf_kernel.py:87 / F.normalize).
+// This kernel scales E by 1/(m_i m_j) and writes the per-column-tile partial sums of s; gpf_diag_fix_kernel
+// adds them up in a fixed order and patches the diagonal of the planes.
+template <bool RSYM, bool FOLD>
 __global__ void __launch_bounds__(256, 3)
 gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
                      const float* __restrict__ Rp, int ldR, const float* __restrict__ coef, int P, int Q,
-                     int symmetric, int n, WPtr Ea, WPtr Ep, float* __restrict__ partial) {
+                     int symmetric, int n, WPtr Ea, WPtr Ep, float* __restrict__ partial,
+                     const float* __restrict__ nrm_a, const float* __restrict__ nrm_p, float eps,
+                     float* __restrict__ rowpart) {
   __shared__ float sa[kPT][kPT + 1], sp[kPT][kPT + 1], sg[kPT][kPT + 1];
   __shared__ float wacc[8][16];
   Poly3 poly;
@@ -601,10 +611,12 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
 #pragma unroll
   for (int t = 0; t < 16; ++t) acc[t] = 0.f;
   float ea_k[4], ep_k[4];
+  float ma_k[4], mp_k[4];     // FOLD: R at the mirrored position (column sums of E * R)
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = ty + 8 * k;
     ea_k[k] = ep_k[k] = 0.f;
+    ma_k[k] = xa[k]; mp_k[k] = xp[k];
     if (i0 + r >= n) continue;   // warp-uniform: a warp owns one row of the tile
     float f, fa, fb, pa[4], pb[4];
     poly.eval_grad(xa[k], xp[k], f, fa, fb, pa, pb);
@@ -631,6 +643,7 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
     }
     float ft, fat, fbt, pat[4], pbt[4];
     poly.eval_grad(sa[tx][r], sp[tx][r], ft, fat, fbt, pat, pbt);
+    ma_k[k] = sa[tx][r]; mp_k[k] = sp[tx][r];
     float dF_ij, dF_ji;
     if (symmetric) {
       const float sgate = (0.5f * (f + ft) >= 0.f) ? 1.f : 0.f;  // clamp(min=0) passes grad at 0
@@ -654,9 +667,44 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
   // stage the tile of E in shared memory; rows leave as 4-column groups (one 8-byte store per plane),
   // the mirror tile as the transposed read of the same staging tile
   __syncthreads();
+  if (FOLD) {
+    const int nt = poly_tiles(n);
+    const long long bn = (long long)blockIdx.y * n;
+    float* rp_a = rowpart + ((long long)blockIdx.y * 2 + 0) * nt * n;
+    float* rp_p = rowpart + ((long long)blockIdx.y * 2 + 1) * nt * n;
+    const int j = j0 + tx;
+    const float ima_c = j < n ? 1.f / fmaxf(nrm_a[bn + j], eps) : 0.f;
+    const float imp_c = j < n ? 1.f / fmaxf(nrm_p[bn + j], eps) : 0.f;
+    float ca = 0.f, cp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + ty + 8 * k;
+      // row sums over this tile's columns (a warp owns the row), column sums over its rows
+      const float ra = warp_sum(ea_k[k] * xa[k]), rpv = warp_sum(ep_k[k] * xp[k]);
+      if (tx == 0 && i < n) { rp_a[(long long)tj * n + i] = ra; rp_p[(long long)tj * n + i] = rpv; }
+      ca = fmaf(ea_k[k], ma_k[k], ca);
+      cp = fmaf(ep_k[k], mp_k[k], cp);
+      const float ima_r = i < n ? 1.f / fmaxf(nrm_a[bn + i], eps) : 0.f;
+      const float imp_r = i < n ? 1.f / fmaxf(nrm_p[bn + i], eps) : 0.f;
+      ea_k[k] *= ima_r * ima_c;
+      ep_k[k] *= imp_r * imp_c;
+    }
+    if (offdiag) {   // block-uniform; sg is free again: rows 0-7 / 8-15 hold the per-warp column sums
+      sg[ty][tx] = ca;
+      sg[8 + ty][tx] = cp;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) { sa[ty + 8 * k][tx] = ea_k[k]; sp[ty + 8 * k][tx] = ep_k[k]; }
   __syncthreads();
+  if (FOLD && offdiag && ty == 0 && j0 + tx < n) {
+    const int nt = poly_tiles(n);
+    float a = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sg[w][tx]; b2 += sg[8 + w][tx]; }
+    rowpart[(((long long)blockIdx.y * 2 + 0) * nt + ti) * n + j0 + tx] = a;
+    rowpart[(((long long)blockIdx.y * 2 + 1) * nt + ti) * n + j0 + tx] = b2;
+  }
   {
     const int r = threadIdx.x >> 3, c = (threadIdx.x & 7) * 4;
     const long long eb = (long long)blockIdx.y * Ea.bs;
@@ -688,6 +736,22 @@ gpf_poly3_bwd_kernel(const float* __restrict__ dG, const float* __restrict__ Ra,
       out[pp * (Q + 1) + qq] = v;
     }
   }
+}
+
+// E''_ii -= [n_i >= eps] * s_i / m_i^2 with s_i = sum over column tiles of the partial row sums (fixed order)
+__global__ void gpf_diag_fix_kernel(const float* __restrict__ rowpart, const float* __restrict__ nrm_a,
+                                    const float* __restrict__ nrm_p, int n, int nt, float eps, WPtr Ea, WPtr Ep) {
+  const int b = blockIdx.y, v = blockIdx.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float nr = (v ? nrm_p : nrm_a)[(long long)b * n + i];
+  if (nr < eps) return;                       // below the clamp: no projection term
+  const float* rp = rowpart + ((long long)b * 2 + v) * nt * n;
+  float s = 0.f;
+  for (int t = 0; t < nt; ++t) s += rp[(long long)t * n + i];
+  const WPtr& E = v ? Ep : Ea;
+  const long long o = (long long)b * E.bs + (long long)i * E.ld + i;
+  wstore(E, o, wload(E, o) - s / (nr * nr));
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int nt,
@@ -1632,21 +1696,47 @@ void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* 
   note_launch();
 }
 int gpf_poly_bwd_blocks(int batch, int n) { return batch * poly_pairs(n); }
+bool gpf_poly_bwd_can_fold(int P, int Q, int n, long long ldR, const W& Ea) {
+  return P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31) && Ea.ld % 4 == 0;
+}
+size_t gpf_poly_bwd_rowpart_floats(int batch, int n) { return (size_t)batch * 2 * poly_tiles(n) * n; }
 void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
                   const float* coef, int P, int Q, int symmetric, int batch, int n, const W& Ea,
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* nrm_a, const float* nrm_p, float eps, float* rowpart) {
   dim3 grid(poly_pairs(n), batch);
+  if (rowpart && gpf_poly_bwd_can_fold(P, Q, n, ldR, Ea)) {
+    // rows of the last (ragged) tile column that no block writes must read as zero
+    cudaMemsetAsync(rowpart, 0, gpf_poly_bwd_rowpart_floats(batch, n) * sizeof(float), st);
+    if (symmetric & 2)
+      gpf_poly3_bwd_kernel<true, true><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric & 1, n,
+                                                             wptr(Ea, prec), wptr(Ep, prec), partial, nrm_a, nrm_p,
+                                                             eps, rowpart);
+    else
+      gpf_poly3_bwd_kernel<false, true><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric & 1, n,
+                                                              wptr(Ea, prec), wptr(Ep, prec), partial, nrm_a, nrm_p,
+                                                              eps, rowpart);
+    note_launch();
+    gpf_diag_fix_kernel<<<dim3((n + 127) / 128, batch, 2), 128, 0, st>>>(rowpart, nrm_a, nrm_p, n, poly_tiles(n), eps,
+                                                                          wptr(Ea, prec), wptr(Ep, prec));
+    note_launch();
+    const int nt = (P + 1) * (Q + 1);
+    reduce_partials_kernel<<<nt, 256, 0, st>>>(partial, nblocks, nt, dcoef);
+    note_launch();
+    return;
+  }
   // bit 1 of `symmetric`: R_a / R_p are exactly symmetric (the fused forward wrote them)
   const bool rsym = (symmetric & 2) != 0;
   symmetric &= 1;
   if (P <= 3 && Q <= 3 && (long long)n * ldR < (1ll << 31) && Ea.ld % 4 == 0) {
     if (rsym)
-      gpf_poly3_bwd_kernel<true><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
-                                                       wptr(Ea, prec), wptr(Ep, prec), partial);
+      gpf_poly3_bwd_kernel<true, false><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
+                                                              wptr(Ea, prec), wptr(Ep, prec), partial, nullptr,
+                                                              nullptr, 0.f, nullptr);
     else
-      gpf_poly3_bwd_kernel<false><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
-                                                        wptr(Ea, prec), wptr(Ep, prec), partial);
+      gpf_poly3_bwd_kernel<false, false><<<grid, 256, 0, st>>>(dG, Ra, Rp, (int)ldR, coef, P, Q, symmetric, n,
+                                                               wptr(Ea, prec), wptr(Ep, prec), partial, nullptr,
+                                                               nullptr, 0.f, nullptr);
   } else {
     gpf_poly_bwd_kernel<kMaxDeg><<<grid, 256, 0, st>>>(dG, Ra, Rp, ldR, coef, P, Q, symmetric, n,
                                                        wptr(Ea, prec), wptr(Ep, prec), partial);

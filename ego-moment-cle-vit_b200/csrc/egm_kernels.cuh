@@ -63,11 +63,17 @@ void rownorm_bwd(const float* x, const float* nrm, const float* dxn, int batch, 
 void gpf_poly_fwd(const float* Ra, const float* Rp, long long ldR, const float* coef, int P, int Q,
                   int symmetric, int batch, int n, float* G, cudaStream_t st);
 // Ea = dRa + dRa^T, Ep = dRp + dRp^T (working matrices), dcoef[(P+1)(Q+1)]
+// `symmetric`: bit 0 = symmetric_enforce, bit 1 = R_a / R_p symmetric bit for bit (fused forward).
+// With `rowpart` (gpf_poly_bwd_rowpart_floats) and gpf_poly_bwd_can_fold(): the backward of F.normalize is
+// folded in - Ea, Ep become E'' with dx = E'' X on the RAW token planes (see gpf_poly3_bwd_kernel).
 void gpf_poly_bwd(const float* dG, const float* Ra, const float* Rp, long long ldR,
                   const float* coef, int P, int Q, int symmetric, int batch, int n, const W& Ea,
                   const W& Ep, float* partial, int nblocks, float* dcoef, int prec,
-                  cudaStream_t st);
+                  cudaStream_t st, const float* nrm_a = nullptr, const float* nrm_p = nullptr,
+                  float eps = 0.f, float* rowpart = nullptr);
 int gpf_poly_bwd_blocks(int batch, int n);
+bool gpf_poly_bwd_can_fold(int P, int Q, int n, long long ldR, const W& Ea);
+size_t gpf_poly_bwd_rowpart_floats(int batch, int n);
 
 // GraphPolynomialFusion.forward in one pass over the tokens (egm_gpf_fused.cu): Gram matrices of both
 // views on tcgen05 from fp32 tokens converted on the fly, cosine scaling + polynomial + clamp in the
