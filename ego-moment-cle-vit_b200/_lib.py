@@ -38,6 +38,7 @@ SIGNATURES = {
     "egm_prof_count": (_I, []),
     "egm_prof_read": (_I, [_I, _P, _P, _P]),
     "egm_gpf_fused_ok": (_I, [_I, _I, _I, _I, _I]),
+    "egm_gpf_raw_planes_ok": (_I, [_I, _I, _I, _I, _I]),
     "egm_gpf_ldr": (_LL, [_I]),
     "egm_gpf_fwd_workspace": (_Z, [_I, _I, _I, _I]),
     "egm_gpf_state_bytes": (_Z, [_I, _I, _I, _I]),

@@ -334,6 +334,13 @@ int egm_gpf_fused_ok(int N, int D, int P, int Q, int prec) {
   return prec != PREC_FP32_SIMT && k::gpf_fused_supported(N, D, P, Q, dummy, dummy) ? 1 : 0;
 }
 
+int egm_gpf_raw_planes_ok(int N, int D, int P, int Q, int prec) {
+  // the fused forward can hand the backward the RAW token planes iff the backward can fold F.normalize
+  // into E (degrees <= 3: the specialised polynomial kernel)
+  const W probe = make_w(nullptr, 1, N, N);
+  return egm_gpf_fused_ok(N, D, P, Q, prec) && k::gpf_poly_bwd_can_fold(P, Q, N, egm_gpf_ldr(N), probe) ? 1 : 0;
+}
+
 int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N, int D, int P, int Q,
                 int cosine, float eps, int symmetric, float* G, float* Ra, float* Rp, float* nrm_a,
                 float* nrm_p, void* xn_state, int prec, void* ws, size_t ws_bytes, egm_stream_t stream) {
@@ -346,10 +353,16 @@ int egm_gpf_fwd(const float* a, const float* p, const float* coef, int B, int N,
   // One fused pass (egm_gpf_fused.cu) whenever the tensor-core modes can address the tokens: nothing
   // but G, the norms and (on request) R_a / R_p is written; the normalised operand planes are not
   // produced (xn_state stays unused and the backward re-derives them).
-  if (prec != PREC_FP32_SIMT && !xn_state && k::gpf_fused_supported(N, D, P, Q, a, p)) {
+  const bool raw_ok = cosine && egm_gpf_raw_planes_ok(N, D, P, Q, prec);
+  if (prec != PREC_FP32_SIMT && (!xn_state || raw_ok) && k::gpf_fused_supported(N, D, P, Q, a, p)) {
     (void)symmetric;   // the fused result is symmetric by construction: F_ij is evaluated once per pair
+    // xn_state (cosine, degrees <= 3): the RAW tokens as operand planes, written by the converter threads;
+    // the caller passes `symmetric | 4` to egm_gpf_bwd, which then folds F.normalize's backward into E
+    Arena xs(xn_state, xn_state ? egm_gpf_state_bytes(B, N, D, prec) : 0);
+    const W Ar = make_w(xs.take(w_bytes(B, N, D)), B, N, D), Pr = make_w(xs.take(w_bytes(B, N, D)), B, N, D);
     EGM_CUDA(k::gpf_fused_fwd(a, p, coef, B, N, D, P, Q, cosine, eps, G, Ra, Rp, egm_gpf_ldr(N), nrm_a,
-                              nrm_p, prec == PREC_BF16X3 ? 3 : 1, st));
+                              nrm_p, prec == PREC_BF16X3 ? 3 : 1, st, xn_state ? &Ar : nullptr,
+                              xn_state ? &Pr : nullptr));
     return EGM_OK;
   }
   EGM_REQUIRE(Ra && Rp, EGM_ERR_ARG, "egm_gpf_fwd: the staged path needs Ra and Rp");
@@ -412,7 +425,13 @@ int egm_gpf_bwd(const float* dG, const float* a, const float* p, const float* co
   // backward of F.normalize is folded into E (k::gpf_poly_bwd): the product with the RAW token planes
   // is the token gradient itself - no [B,N,D] rownorm_bwd pass, no fp32 round trip of d x-hat.
   static const bool fold_off = []() { const char* e = getenv("EGM_GPF_FOLD"); return e && e[0] == '0'; }();
-  const bool fold = cosine && !xn_state && !fold_off && k::gpf_poly_bwd_can_fold(P, Q, N, ldR, Ea);
+  // bit 2 of `symmetric`: xn_state holds the RAW token planes (fused forward in training mode)
+  const bool raw_planes = xn_state && (symmetric & 4);
+  symmetric &= 3;
+  EGM_REQUIRE(!raw_planes || (cosine && k::gpf_poly_bwd_can_fold(P, Q, N, ldR, Ea)), EGM_ERR_ARG,
+              "egm_gpf_bwd: raw token planes need cosine similarity and degrees <= 3");
+  const bool fold = raw_planes ||
+                    (cosine && !xn_state && !fold_off && k::gpf_poly_bwd_can_fold(P, Q, N, ldR, Ea));
   k::gpf_poly_bwd(dG, Ra, Rp, ldR, coef, P, Q, symmetric, B, N, Ea, Ep, partial, nblocks, dcoef, prec, st, nrm_a,
                   nrm_p, eps, fold ? rowpart : nullptr);
   EGM_LAUNCHED();

@@ -67,6 +67,11 @@ struct FusedParams {
   float* Rp;
   long long ldR;
   float* nrm[2];          // [B][N]
+  // optional (training): the RAW tokens as bf16 hi/lo operand planes [B][N][ld_pl] for the backward's
+  // dx = E'' X product - the converter threads hold exactly these values in registers
+  __nv_bfloat16* xpl[2];
+  long long pl_lo_off;    // elements from a hi plane to its lo plane
+  int ld_pl;
 };
 
 template <int MD>
@@ -276,6 +281,19 @@ __global__ void __launch_bounds__(kThreadsF, 1) gpf_fused_fwd_kernel(const __gri
                 if (p.npass == 3)
                   ptx::sts128(dst + kPlane + off, lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
               }
+              // training: the same values leave as the backward's operand planes (row tile 0 covers every row)
+              if (p.xpl[u & 1] && r == 0 && t < N) {
+                const int kcol = (u >> 1) * 32 + 16 * hh;
+                __nv_bfloat16* gp = p.xpl[u & 1] + ((long long)b * N + t) * p.ld_pl + kcol;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  if (kcol + 8 * c < p.ld_pl) {
+                    *reinterpret_cast<uint4*>(gp + 8 * c) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+                    if (p.npass == 3)
+                      *reinterpret_cast<uint4*>(gp + p.pl_lo_off + 8 * c) =
+                          make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+                  }
+              }
             }
             ssq[u & 1] += (a0 + a1) + (a2 + a3);
           }
@@ -457,9 +475,16 @@ bool gpf_fused_supported(int n, int d, int P, int Q, const float* a, const float
 
 cudaError_t gpf_fused_fwd(const float* a, const float* p, const float* coef, int batch, int n, int d, int P,
                           int Q, int cosine, float eps, float* G, float* Ra, float* Rp, long long ldR,
-                          float* nrm_a, float* nrm_p, int npass, cudaStream_t st) {
+                          float* nrm_a, float* nrm_p, int npass, cudaStream_t st, const W* xa_raw,
+                          const W* xp_raw) {
   FusedParams fp;
   memset(&fp, 0, sizeof(fp));
+  if (xa_raw && xp_raw) {
+    fp.xpl[0] = static_cast<__nv_bfloat16*>(xa_raw->base);
+    fp.xpl[1] = static_cast<__nv_bfloat16*>(xp_raw->base);
+    fp.pl_lo_off = (long long)xa_raw->batch * xa_raw->rows * xa_raw->ld;
+    fp.ld_pl = (int)xa_raw->ld;
+  }
   fp.B = batch; fp.N = n; fp.D = d;
   fp.NP = (n + 15) / 16 * 16;
   fp.P = P; fp.Q = Q; fp.cosine = cosine; fp.npass = npass; fp.eps = eps;

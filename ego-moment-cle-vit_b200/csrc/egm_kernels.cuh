@@ -79,9 +79,12 @@ size_t gpf_poly_bwd_rowpart_floats(int batch, int n);
 // views on tcgen05 from fp32 tokens converted on the fly, cosine scaling + polynomial + clamp in the
 // epilogue. Ra / Rp (optional, [B][n][ldR]) are written when the backward will need them.
 bool gpf_fused_supported(int n, int d, int P, int Q, const float* a, const float* p);
+// xa_raw / xp_raw (optional working matrices [B][n][d]): the RAW tokens as operand planes, for a backward
+// that folds the normalisation into E (gpf_poly_bwd with rowpart).
 cudaError_t gpf_fused_fwd(const float* a, const float* p, const float* coef, int batch, int n, int d, int P,
                           int Q, int cosine, float eps, float* G, float* Ra, float* Rp, long long ldR,
-                          float* nrm_a, float* nrm_p, int npass, cudaStream_t st);
+                          float* nrm_a, float* nrm_p, int npass, cudaStream_t st, const W* xa_raw = nullptr,
+                          const W* xp_raw = nullptr);
 
 // deg = G 1 ; s = rsqrt(max(deg, eps))
 void degree(const float* G, int batch, int n, float eps, float* deg, float* s, cudaStream_t st);

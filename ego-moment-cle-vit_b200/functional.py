@@ -104,6 +104,10 @@ def _p(t):
 
 # --------------------------------------------------------------------------- GPF
 _gpf_recompute = os.environ.get("EGM_GPF_RECOMPUTE", "0") == "1"
+# EGM_GPF_RAW_PLANES=1: the fused forward also writes the raw tokens as operand planes for the backward
+# (saves the backward's 2 x 54 us re-derivation, costs the forward 137 us of scattered 16-byte stores at
+# B=256: measured a net loss of 30 us per step, so it is off by default)
+_gpf_raw_planes = os.environ.get("EGM_GPF_RAW_PLANES", "0") == "1"
 
 
 class _GPFFunction(Function):
@@ -127,7 +131,10 @@ class _GPFFunction(Function):
             coef_c = coef.detach().contiguous()
             # staged path: keep the normalised tokens (GEMM operand planes, 2 x [B,N,D]) for the backward
             # when one will run; EGM_GPF_RECOMPUTE=1 trades them for a re-normalisation pass in the backward
-            keep = need_grad and not _gpf_recompute and not fused
+            # fused path: the RAW token planes, when the backward can fold F.normalize into E (cosine, degrees <= 3)
+            raw = (_gpf_raw_planes and fused and bool(cosine)
+                   and bool(L.egm_gpf_raw_planes_ok(N, D, P, Q, prec)))
+            keep = need_grad and not _gpf_recompute and (raw or not fused)
             xn = _ws(L.egm_gpf_state_bytes(B, N, D, prec), dev) if keep else None
             ws = _ws(L.egm_gpf_fwd_workspace(B, N, D, prec) if not (keep or fused) else 16, dev)
             _lib.check(L.egm_gpf_fwd(a.data_ptr(), p.data_ptr(), coef_c.data_ptr(), B, N, D, P, Q,
@@ -137,7 +144,8 @@ class _GPFFunction(Function):
         if need_grad:
             ctx.save_for_backward(a, p, coef_c, Ra, Rp, nrm, *([xn] if keep else []))
         # bit 1: R_a / R_p are symmetric bit for bit (fused forward) - the backward evaluates each pair once
-        ctx.cfg = (int(cosine), float(eps), int(symmetric) | (2 if fused else 0), prec)
+        # bit 2: the saved planes are the raw tokens (see egm_gpf_raw_planes_ok)
+        ctx.cfg = (int(cosine), float(eps), int(symmetric) | (2 if fused else 0) | (4 if (fused and keep) else 0), prec)
         return G
 
     @staticmethod

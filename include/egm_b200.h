@@ -82,6 +82,11 @@ int egm_prof_read(int i, float* ms, double* flops, int* dims);
  * written by the fused pass are symmetric bit for bit; pass `symmetric | 2` to egm_gpf_bwd to let the
  * backward evaluate each (i,j)/(j,i) pair once. */
 int egm_gpf_fused_ok(int N, int D, int P, int Q, int prec);
+/* != 0: egm_gpf_fwd (fused, cosine similarity) may also be given xn_state; it then receives the RAW tokens
+ * as GEMM operand planes (written by the threads that convert them for the Gram products), and the caller
+ * passes `symmetric | 2 | 4` to egm_gpf_bwd, which folds the backward of F.normalize into E and needs
+ * neither a re-normalisation pass nor a rownorm_bwd pass over [B,N,D]. */
+int egm_gpf_raw_planes_ok(int N, int D, int P, int Q, int prec);
 long long egm_gpf_ldr(int N);
 size_t egm_gpf_state_bytes(int B, int N, int D, int prec);
 size_t egm_gpf_fwd_workspace(int B, int N, int D, int prec);

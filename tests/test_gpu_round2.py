@@ -352,14 +352,16 @@ def test_strict_fp32_linear_runs_on_the_library(pkg, dev):
 
 
 # --------------------------------------- F.normalize backward folded into E (no rownorm_bwd pass)
-@pytest.mark.parametrize("shape,recompute", [((3, 50, 136), False), ((2, 197, 768), False), ((2, 21, 30), True),
-                                             ((1, 230, 64), True)])
+@pytest.mark.parametrize("shape,recompute,raw", [((3, 50, 136), False, False), ((2, 197, 768), False, False),
+                                                 ((3, 50, 136), False, True), ((2, 197, 768), False, True),
+                                                 ((2, 21, 30), True, False), ((1, 230, 64), True, False)])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_gpf_backward_with_the_normalisation_folded_into_E(pkg, dev, shape, recompute, mode):
+def test_gpf_backward_with_the_normalisation_folded_into_E(pkg, dev, shape, recompute, raw, mode):
     """egm_gpf_bwd without kept operand planes: E'' = (E - diag(s)) / (m_i m_j), dx = E'' X on the raw token
     planes (csrc/egm_kernels.cu, gpf_poly3_bwd_kernel FOLD). Token / coefficient gradients vs the oracle, with
     a zero token row (below the eps clamp: no projection term) in the batch. The last two shapes cannot take
-    the fused forward (D % 4 != 0, N > 208) and exercise the fold after the staged forward."""
+    the fused forward (D % 4 != 0, N > 208) and exercise the fold after the staged forward; `raw` lets the
+    fused forward write the raw token planes itself (EGM_GPF_RAW_PLANES) instead of the backward re-deriving them."""
     EF = pkg.functional
     B, N, D = shape
     a0, p0 = make_inputs(B, N, D, seed=7)
@@ -369,8 +371,8 @@ def test_gpf_backward_with_the_normalisation_folded_into_E(pkg, dev, shape, reco
     dG = torch.randn(B, N, N, generator=g)
     fw = O.gpf_forward(npy(a0), npy(p0), npy(alpha))
     da, dp, dal = O.gpf_backward(npy(a0), npy(p0), npy(alpha), npy(dG))
-    prev = EF._gpf_recompute
-    EF._gpf_recompute = recompute
+    prev = (EF._gpf_recompute, EF._gpf_raw_planes)
+    EF._gpf_recompute, EF._gpf_raw_planes = recompute, raw
     try:
         with EF.precision(mode):
             a = a0.to(dev).requires_grad_(True)
@@ -379,12 +381,12 @@ def test_gpf_backward_with_the_normalisation_folded_into_E(pkg, dev, shape, reco
             G = EF.gpf_fused_graph(a, p, torch.nn.functional.softplus(al))
             (G * dG.to(dev)).sum().backward()
     finally:
-        EF._gpf_recompute = prev
+        EF._gpf_recompute, EF._gpf_raw_planes = prev
     to, tg = (1e-3, 1e-3) if mode == "fp32" else (2e-2, 6e-2)
     errs = {"G": rel_err(npy(G), fw["G"]), "d_anchor": rel_err(npy(a.grad), da), "d_positive": rel_err(npy(p.grad), dp),
             "d_alpha": rel_err(npy(al.grad), dal),
             "zero_row": rel_err(npy(a.grad)[0, 3], da[0, 3])}
-    report(f"gpf_fold:{shape}:{mode}", **errs)
+    report(f"gpf_fold:{shape}:{mode}:raw={int(raw)}", **errs)
     assert errs["G"] < to
     assert errs["d_anchor"] < tg and errs["d_positive"] < tg and errs["d_alpha"] < tg
     assert errs["zero_row"] < 10 * tg
