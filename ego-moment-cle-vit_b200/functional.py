@@ -666,7 +666,6 @@ class _FeatureTailFunction(Function):
         ctx.save_for_backward(y, stats, *([gamma] if gamma is not None else []),
                               *([beta] if beta is not None else []))
         ctx.cfg = (int(training), float(drop_p), int(seed), gamma is not None, beta is not None)
-        ctx.mark_non_differentiable(*[t for t in (run_mean, run_var) if t is not None])
         return out
 
     @staticmethod
@@ -692,10 +691,15 @@ class _FeatureTailFunction(Function):
         return dy, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def _draw_seed() -> int:
-    """A 63-bit dropout seed from torch's default CPU generator: host-side, no launch, no sync, and
-    reproducible under torch.manual_seed."""
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+def _draw_seed(device) -> int:
+    """A dropout seed drawn the way torch's own CUDA dropout draws its randomness: from the device's
+    default Philox generator - (initial seed, current offset) - advancing the offset. Host-side, no
+    launch, no sync; `torch.manual_seed` resets it, so runs are reproducible; the CPU generator is not
+    touched (the reference's dropout does not touch it either)."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    off = gen.get_offset()
+    gen.set_offset(off + 4)                      # Philox offsets move in multiples of 4
+    return ((gen.initial_seed() * 0x9E3779B97F4A7C15) ^ (off * 0xBF58476D1CE4E5B9 + 0x94D049BB133111EB)) & (2 ** 63 - 1)
 
 
 def feature_tail(y, layers):
@@ -703,8 +707,9 @@ def feature_tail(y, layers):
     195-200) - as one kernel each way. `layers` are the nn.Modules themselves: their parameters,
     running statistics (updated in place like nn.BatchNorm1d, incl. num_batches_tracked) and
     train/eval flags are used as they are, so state_dicts are unaffected. The dropout keep-mask comes
-    from a counter-based hash seeded from torch's CPU generator, not from torch's CUDA Philox stream:
-    same distribution, different bits. Any other layer combination is applied layer by layer."""
+    from a counter-based hash whose seed is derived from the device's default Philox generator state
+    (`_draw_seed`: reproducible under torch.manual_seed, advances the CUDA offset like torch's dropout,
+    leaves the CPU generator alone); the mask bits are not torch's: same distribution, different bits. Any other layer combination is applied layer by layer."""
     layers = list(layers)
     nn = torch.nn
     if not (len(layers) == 3 and isinstance(layers[0], nn.BatchNorm1d) and isinstance(layers[1], nn.GELU)
@@ -732,7 +737,7 @@ def feature_tail(y, layers):
             y = layer(y)
         return y
     p = float(drop.p) if drop.training else 0.0
-    seed = _draw_seed() if p > 0.0 else 0
+    seed = _draw_seed(y.device) if p > 0.0 else 0
     # `training` selects batch statistics; dropout is gated by its own p
     upd_mean, upd_var = (run_mean, run_var) if (bn.training or not use_batch) else (None, None)
     return _FeatureTailFunction.apply(y, bn.weight, bn.bias, upd_mean, upd_var, use_batch, momentum or 0.0,

@@ -298,8 +298,10 @@ def test_feature_tail_dropout_contract(pkg, dev):
     y = torch.randn(M, N, device=dev) + 2.0
     nodrop = EF.feature_tail(y, [layers[0], layers[1], torch.nn.Dropout(0.0).train()])
     torch.manual_seed(11)
+    cpu_state = torch.get_rng_state()
     yy = y.clone().requires_grad_(True)
     out = EF.feature_tail(yy, layers)
+    assert torch.equal(torch.get_rng_state(), cpu_state)       # the CPU generator is left alone
     kept = out != 0
     rate = float(kept.float().mean())
     live = float((nodrop != 0).float().mean())
