@@ -696,6 +696,10 @@ def _draw_seed(device) -> int:
     default Philox generator - (initial seed, current offset) - advancing the offset. Host-side, no
     launch, no sync; `torch.manual_seed` resets it, so runs are reproducible; the CPU generator is not
     touched (the reference's dropout does not touch it either)."""
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("train-mode dropout inside a CUDA-graph capture: the keep-mask seed is a launch constant "
+                           "of this library's kernel, every replay would reuse one mask - capture with the "
+                           "Dropout modules in eval mode / p = 0, or keep this layer outside the graph")
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     off = gen.get_offset()
     gen.set_offset(off + 4)                      # Philox offsets move in multiples of 4
