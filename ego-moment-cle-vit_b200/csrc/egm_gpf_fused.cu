@@ -5,7 +5,7 @@
 //
 // One persistent CTA per SM walks the images. For an image it streams both token matrices from HBM
 // exactly once:
-//   warp 0      TMA producer: fp32 boxes {32 features x NP/2 tokens} x 2 of one view into a 3-slot
+//   warp 0      TMA producer: fp32 boxes {32 features x NP/2 tokens} x 2 of one view into a 5-slot
 //               staging ring (128B swizzle), mbarrier complete_tx
 //   warps 2..9  converters: one token row per thread - read the fp32 row slice, add it to the row's
 //               running sum of squares (the norm of F.normalize, exact fp32), split into bf16 hi/lo
