@@ -36,6 +36,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "egm_gemm.h"
 #include "egm_ptx.cuh"
 
@@ -846,9 +848,11 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
     configured_dev = dev;
   }
   // one counter pair of the device-global pool per launch, round-robin (see g_sched_pool)
+  // (the sequence number is process-wide: two host threads launching on the same device must never
+  // share a slot, or their kernels would split one tile list between them)
   static thread_local unsigned* pool = nullptr;
   static thread_local int pool_dev = -1;
-  static thread_local unsigned seq = 0;
+  static std::atomic<unsigned> seq{0};
   if (pool_dev != dev) {
     void* sym = nullptr;
     e = cudaGetSymbolAddress(&sym, g_sched_pool);
@@ -859,7 +863,7 @@ cudaError_t launch2(const TcParams& p, cudaStream_t stream) {
   // EGM_SCHED=0: static round-robin tiles (A/B switch)
   static const bool dynamic = []() { const char* e = getenv("EGM_SCHED"); return !(e && e[0] == '0'); }();
   TcParams q = p;
-  q.sched = dynamic ? pool + 2u * ((seq++) % (unsigned)kSchedPool) : nullptr;
+  q.sched = dynamic ? pool + 2u * (seq.fetch_add(1u, std::memory_order_relaxed) % (unsigned)kSchedPool) : nullptr;
   int sms = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
