@@ -325,6 +325,83 @@ def test_gradient_accumulation_contract_gloo():
         assert np.allclose(got0, 0.5 * p_.grad.numpy(), atol=1e-6)
 
 
+def _gloo_early_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    load_pkg()
+    d = importlib.import_module("ego-moment-cle-vit_b200.dist")
+    EF = importlib.import_module("ego-moment-cle-vit_b200.functional")
+    torch.manual_seed(0)
+    big = torch.nn.Parameter(torch.zeros(4, 50))           # stands in for second_net.0.weight
+    small = torch.nn.Parameter(torch.zeros(3))
+    buckets = d.GradBuckets([small, big], bucket_bytes=64, chunk_bytes=256)      # hooks on, chunked
+    assert EF.get_early_grad_hook() == buckets.early_reduce
+    # what the fused head's backward does: dW exists, hand it over, keep computing, wait, return it
+    g_big = torch.full((4, 50), float(rank + 1))
+    pend = EF.get_early_grad_hook()(big.data_ptr(), g_big)
+    assert pend is not None and len(pend.works) > 1         # several chunks in flight
+    unknown = EF.get_early_grad_hook()(12345, torch.zeros(2))
+    pend.wait()
+    # autograd's accumulation (steals the tensor) + the post-accumulate hooks
+    big.grad = g_big
+    buckets._on_grad(big)
+    small.grad = torch.full((3,), float(10 * (rank + 1)))
+    buckets._on_grad(small)
+    buckets.reduce()
+    # under no_sync() the reducer must not take the gradient early (local sums are accumulated instead)
+    with buckets.no_sync():
+        declined = EF.get_early_grad_hook()(big.data_ptr(), torch.ones(4, 50))
+    q.put((rank, unknown is None, declined is None, big.grad.numpy().copy(), small.grad.numpy().copy()))
+    buckets.close()
+    assert EF.get_early_grad_hook() is None
+    dist.destroy_process_group()
+
+
+def test_early_gradient_hand_over_protocol_gloo():
+    """dist.GradBuckets.early_reduce - the hook the fused MomentHead operator calls with dW of its Linear
+    before it enqueues the Newton-Schulz backward - averaged in chunks, excluded from its bucket's later
+    all-reduce, declined for unknown tensors and under no_sync()."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_early_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, unknown_declined, nosync_declined, gb, gs in res:
+        assert unknown_declined and nosync_declined
+        assert np.allclose(gb, 1.5) and np.allclose(gs, 15.0)      # mean over the two ranks, once
+
+
+def test_bench_workload_switches():
+    """bench.py --config 3 / 4 / 5 select BASELINE.json's other workloads and name them in the line."""
+    import bench
+    argv = sys.argv
+    try:
+        for flags, name, checks in (
+                ([], "configs[1]", dict(tokens=197, d_in=768, batch=256, third_order=False)),
+                (["--config", "3"], "configs[2]", dict(third_order=True, sketch_dim=8192)),
+                (["--config", "5", "--degree", "2", "1"], "configs[4]", dict(tokens=144, d_in=1024, degree=[2, 1])),
+                (["--config", "4"], "configs[3]", dict(batch=64, degree=[2, 2]))):
+            sys.argv = ["bench.py"] + flags
+            args = bench.parse()
+            for k, v in checks.items():
+                assert getattr(args, k) == v, (flags, k, getattr(args, k))
+            assert bench.workload_name(args) == name
+            cfg = bench.workload_config(args)
+            assert cfg["workload"].startswith(name)
+            if args.third_order:
+                assert "tensor_sketch.sketch_dim" in cfg["third_order"]["oracle_patch"]
+    finally:
+        sys.argv = argv
+        bench.N_TOK, bench.D_IN, bench.DEGS = 197, 768, (3, 3)
+
+
 def test_shard_bounds_cover_batch():
     d = importlib.import_module("ego-moment-cle-vit_b200.dist")
     for B in (1, 7, 8, 256, 257):
