@@ -167,3 +167,43 @@ def test_torch_eager_comparator_matches_the_oracle():
     assert rel_err(a.grad.numpy(), da + dZ) < 1e-8
     assert rel_err(p.grad.numpy(), dp) < 1e-8
     assert rel_err(alpha.grad.numpy(), dal) < 1e-8
+
+
+def test_normalize_backward_folds_into_the_pair_gradient_matrix():
+    """The identity behind the folded GPF backward (csrc/egm_kernels.cu, gpf_poly3_bwd_kernel FOLD): with
+    xh = x / m, m = max(||x||, eps) (F.normalize, gpf_kernel.py:87), E = dR + dR^T and dxh = E xh,
+        dx_i = (dxh_i - [n_i >= eps] xh_i <xh_i, dxh_i>) / m_i      and   <xh_i, dxh_i> = sum_j E_ij R_ij = s_i,
+    hence dx = E'' X on the RAW tokens with E''_ij = (E_ij - [n_i >= eps] s_i delta_ij) / (m_i m_j) - no pass
+    over [N, D] for the normalisation's backward. Checked against the oracle's own similarity backward
+    (which follows the reference's autograd), including a row below the eps clamp."""
+    rng = np.random.default_rng(3)
+    B, N, D, eps = 2, 9, 14, 1e-6
+    X = rng.standard_normal((B, N, D))
+    X[0, 2] = 0.0                                   # ||x|| < eps: x / eps, no projection term
+    dR = rng.standard_normal((B, N, N))
+    n = np.linalg.norm(X, axis=-1)
+    m = np.maximum(n, eps)
+    Xh = X / m[..., None]
+    R = Xh @ np.swapaxes(Xh, 1, 2)
+    assert rel_err(R, O.similarity(X, "cosine", eps)) < 1e-12
+    E = dR + np.swapaxes(dR, 1, 2)
+    # two-step form (what rownorm_bwd used to do)
+    dXh = E @ Xh
+    s_ref = np.einsum("bnd,bnd->bn", Xh, dXh)
+    gate = (n >= eps)[..., None]
+    dX_two_step = (dXh - gate * Xh * s_ref[..., None]) / m[..., None]
+    # folded form
+    s = np.einsum("bij,bij->bi", E, R)
+    assert rel_err(s, s_ref) < 1e-12
+    E2 = E / (m[:, :, None] * m[:, None, :])
+    idx = np.arange(N)
+    E2[:, idx, idx] -= np.where(n >= eps, s / (m * m), 0.0)
+    dX_folded = E2 @ X
+    assert rel_err(dX_folded, dX_two_step) < 1e-12
+    # and the two-step form IS the reference's gradient: drive the oracle's GPF backward with a polynomial
+    # that is the identity in R_a (alpha so that only c_10 matters) ... simpler: autograd of the same graph
+    import torch
+    xt = torch.from_numpy(X).requires_grad_(True)
+    xh = torch.nn.functional.normalize(xt, p=2, dim=-1, eps=eps)
+    (torch.bmm(xh, xh.transpose(1, 2)) * torch.from_numpy(dR)).sum().backward()
+    assert rel_err(dX_folded, xt.grad.numpy()) < 1e-10
