@@ -427,8 +427,27 @@ def moment_head_linear(tokens, graph, weight, bias, num_iterations, *, eps=1e-5,
         raise RuntimeError(f"linear: weight {tuple(w.shape)} does not match d_in={D}")
     b = _require_cuda_f32("bias", bias, 1) if bias is not None else None
     flags = _lib.MHD_SYMMETRIC_GRAPH if (not lowrank and graph_is_symmetric(graph)) else 0
-    return _MomentHeadLinearFunction.apply(Z, G, w, b, int(num_iterations), eps, third_order, lowrank, prec,
-                                           flags)
+    args = (w, b, int(num_iterations), eps, third_order, lowrank, prec, flags)
+    # Inference: nothing is kept for a backward, yet the operator's working state is the training state
+    # (13 D x D matrices per image at K = 5). The path is independent per image and its results are
+    # bit-identical under batch sharding (tests), so a large no-grad batch is evaluated in slices whose
+    # state stays under `_nograd_state_limit` instead of allocating all of it at once.
+    B = Z.shape[0]
+    need_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (Z, G, w, b))
+    if not need_grad and B > 1:
+        L = _lib.load()
+        per = (L.egm_mlr_state_bytes if lowrank else L.egm_mhd_state_bytes)(1, Z.shape[1], D, int(num_iterations), prec)
+        step = max(1, int(_nograd_state_limit // max(per, 1)))
+        if step < B:
+            outs = [_MomentHeadLinearFunction.apply(Z[i:i + step], G[i:i + step], *args) for i in range(0, B, step)]
+            if third_order:
+                return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+            return torch.cat(outs)
+    return _MomentHeadLinearFunction.apply(Z, G, *args)
+
+
+# working-state budget of a no-grad call of the fused head (bytes); EGM_NOGRAD_STATE_GB overrides
+_nograd_state_limit = float(os.environ.get("EGM_NOGRAD_STATE_GB", "8.5")) * 2 ** 30
 
 
 # ---- exact-symmetry tag of a graph tensor ---------------------------------------------------

@@ -392,3 +392,31 @@ def test_gpf_backward_with_the_normalisation_folded_into_E(pkg, dev, shape, reco
     assert errs["G"] < to
     assert errs["d_anchor"] < tg and errs["d_positive"] < tg and errs["d_alpha"] < tg
     assert errs["zero_row"] < 10 * tg
+
+
+def test_large_nograd_batches_are_evaluated_in_slices(pkg, dev):
+    """a no-grad call of the fused head must not allocate the whole training state. Above the
+    working-state budget the batch is evaluated slice by slice - bit-identical to the single call."""
+    EF = pkg.functional
+    torch.manual_seed(0)
+    gpf = pkg.GraphPolynomialFusion(2, 2).to(dev)
+    head = pkg.MomentHead(136, 16, use_third_order=True, isqrt_iterations=3, sketch_dim=64).to(dev).eval()
+    a, p = (t.to(dev) for t in make_inputs(7, 50, 136))
+    prev = EF._nograd_state_limit
+    try:
+        with torch.no_grad():
+            G = gpf(a, p)
+            ref = head(a, G)
+            torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.max_memory_allocated()
+            EF._nograd_state_limit = 1.0          # one image per slice
+            out = head(a, G)
+        # with grad enabled the call is never sliced (the saved state belongs to one autograd node)
+        a2 = a.clone().requires_grad_(True)
+        EF._nograd_state_limit = 1.0
+        out2 = head(a2, gpf(a2, p))
+        out2.sum().backward()
+    finally:
+        EF._nograd_state_limit = prev
+    assert torch.equal(out, ref)
+    assert rel_err(npy(out2), npy(ref)) < 1e-6 and a2.grad is not None
